@@ -1,0 +1,135 @@
+// kernels.h -- internal interface between the learner orchestration (learner.cu) and the kernel
+// launchers (layers.cu, elementwise.cu, vtrace.cu, optimizer.cu).  Not part of the C-ABI.
+#pragma once
+#include "common.cuh"
+
+namespace drl {
+
+// Offsets (in floats) of each tensor inside the padded flat parameter / gradient / slot vectors.
+// Order = TF1 variable-creation order; every bias directly follows its
+// kernel (kernel sizes are multiples of 4) and is padded up to a multiple of 4 floats so that all
+// kernels start 16-byte aligned.  [w ; b] therefore forms one contiguous [(K+1), N] matrix, which
+// is what the weight-gradient GEMMs write (bias gradient = column sum of dY in row K).
+struct ParamLayout {
+  int A;
+  int64_t conv1_w, conv1_b, conv2_w, conv2_b, conv3_w, conv3_b;
+  int64_t emb1_w, emb1_b, emb2_w, emb2_b;
+  int64_t lstm_w, lstm_b;
+  int64_t actor1_w, actor1_b, actor2_w, actor2_b, actor3_w, actor3_b;
+  int64_t critic1_w, critic1_b, critic2_w, critic2_b, critic3_w, critic3_b;
+  int64_t padded_total;   // floats in the padded vector (multiple of 4)
+  int64_t packed_total;   // floats in the TF-flat (API) vector
+  static constexpr int kNumTensors = 24;
+  int64_t packed_off[kNumTensors], padded_off[kNumTensors], count[kNumTensors];
+  void init(int num_action);
+};
+
+struct Inputs {          // one device staging slot, caller's batch-major layout
+  const uint8_t* frames; // [B,T,84,84,4]
+  const float* reward;   // [B,T]
+  const int32_t* action; // [B,T]
+  const uint8_t* done;   // [B,T]
+  const float* mu;       // [B,T,A]
+  const int32_t* pa;     // [B,T]
+  const float* h0;       // [B,T,256]
+  const float* c0;       // [B,T,256]
+};
+
+struct Acts {            // forward activations, time-major rows m = t*B + b, M = B*T rows
+  float* a1;             // [M,20,20,32]
+  float* a2;             // [M,9,9,64]
+  float* a3;             // [M,3136]
+  float* e1;             // [A,256]  relu(emb1)
+  float* table;          // [A,256]  action-embedding table
+  float* zpart;          // [SPLITS][M,1024] LSTM pre-activation partial sums
+  float* gates;          // [M,4,256] sigmoid(i), tanh(j), sigmoid(f+1), sigmoid(o)
+  float* c1;             // [M,256]
+  float* tc1;            // [M,256] tanh(c1)
+  float* h1;             // [M,256]
+  float* hid1;           // [2][M,256] actor/critic hidden 1
+  float* hid2;           // [2][M,256] actor/critic hidden 2
+  float* logits;         // [M,A]
+  float* policy;         // [M,A]
+  float* value;          // [M]
+};
+
+struct Bwd {             // backward workspace, Mb = B*(T-2) rows
+  float* dlogits;        // [Mb,32] (columns >= A stay zero)
+  float* dv;             // [Mb,32] (column 0 = dL/dV, others stay zero)
+  float* dhid2;          // [2][Mb,256]
+  float* dhid1;          // [2][Mb,256]
+  float* dh_part;        // [2][Mb,256] actor and critic contributions to dL/dh1
+  float* dz;             // [Mb,1024]
+  float* da3;            // [Mb,3136]
+  float* du;             // [Mb,256]
+  float* dpre2;          // [A,256]
+  float* dpre1;          // [A,256]
+  float* da2;            // [Mb,9,9,64]
+  float* da1;            // [Mb,20,20,32]
+  float* wg_part;        // split-K partial slabs for the conv weight gradients
+  size_t wg_part_floats;
+};
+
+struct VtraceOut {       // parity taps, batch-major [B, T-2]
+  float *vs, *clipped_rho, *vs_plus_1, *pg_adv;
+  float* loss_partials;  // [nblk,3]
+  unsigned int* ticket;  // last-block counter
+  float* loss_sums;      // [4] pi, baseline, entropy, (pad) -- tail of the gradient bucket
+};
+
+constexpr int kLstmSplits = 4;
+
+// Per-kernel device timing (learner.cu): when a profile run is active, prof_mark records a CUDA event
+// on the launching stream before each named launch; otherwise it is a no-op.
+void prof_mark(cudaStream_t s, const char* name);
+
+// ---- layers.cu ----------------------------------------------------------------------------
+int net_forward(cudaStream_t s, const ParamLayout& pl, const float* params, const Inputs& in, const Acts& act,
+                int B, int T);
+int net_backward(cudaStream_t s, const ParamLayout& pl, const float* params, float* grads, const Inputs& in,
+                 const Acts& act, const Bwd& bwd, int B, int T);
+size_t wgrad_partial_floats(int B, int T);
+int forward_launch_count();
+int backward_launch_count();
+
+// ---- elementwise.cu -----------------------------------------------------------------------
+int emb_forward(cudaStream_t s, const float* w1, const float* b1, const float* w2, const float* b2, float* e1,
+                float* table, int A);
+int lstm_gates_forward(cudaStream_t s, const float* zpart, int nsplit, const float* bias, const float* c0,
+                       float* gates, float* c1, float* tc1, float* h1, int M, int B, int T);
+int heads_out_forward(cudaStream_t s, const float* hid2_actor, const float* hid2_critic, const float* w5,
+                      const float* b5, const float* w8, const float* b8, float* logits, float* policy,
+                      float* value, int M, int A);
+int heads_out_backward(cudaStream_t s, const float* dlogits, const float* dv, const float* w5, const float* w8,
+                       const float* hid2_actor, const float* hid2_critic, float* dhid2_actor, float* dhid2_critic,
+                       int Mb, int A);
+int lstm_gates_backward(cudaStream_t s, const float* dh_part, size_t part_stride, const float* gates,
+                        const float* tc1, const float* c0, float* dz, int Mb, int B, int T);
+int emb_backward(cudaStream_t s, const float* du, const int32_t* pa, const float* e1, const float* table,
+                 const float* w2, float* dpre2, float* dpre1, float* g_w1, float* g_b1, float* g_w2, float* g_b2,
+                 int Mb, int B, int T, int A);
+int splitk_reduce(cudaStream_t s, const float* part, size_t slab, int nsplit, float* out, size_t n);
+
+// ---- vtrace.cu ----------------------------------------------------------------------------
+struct VtraceCfg {
+  float discount, baseline_coef, entropy_coef;
+  int reward_clipping;
+};
+int vtrace_losses(cudaStream_t s, const VtraceCfg& cfg, const float* policy, const float* value, const Inputs& in,
+                  const VtraceOut& out, float* dlogits, float* dv, int B, int T, int A);
+
+// ---- optimizer.cu -------------------------------------------------------------------------
+struct OptState {
+  float* params; float* ms; float* grads;   // padded flat vectors
+  int64_t n;                                 // padded_total (multiple of 4)
+  float* norm_partials; int nblk;
+  long long* step;                           // device global_step
+  float* lr_cur;                             // device scalar
+  float* out;                                // device [8]: pi, baseline, entropy, lr, grad_norm, total, step_lo, step_hi
+  const float* loss_sums;                    // bucket tail
+  float start_lr, end_lr; double learning_frame;
+  float clip_norm, baseline_coef, entropy_coef;
+};
+int optimizer_apply(cudaStream_t s, const OptState& o);
+
+}  // namespace drl

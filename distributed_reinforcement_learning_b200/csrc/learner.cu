@@ -1,0 +1,644 @@
+// learner.cu -- the learner handle behind the C-ABI (include/drl_b200.h): owns parameters, RMSProp
+// slots, the gradient bucket, activations, device staging slots, a compute and a copy stream.
+// Replaces impala.Agent's learner graph and Agent.train (agent/impala.py:11-103,132-148).
+#include <stdarg.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+
+namespace drl {
+
+static thread_local char g_err[1024] = {0};
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+// ---- per-kernel profiler -------------------------------------------------------------------
+struct Profiler {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;
+  std::vector<const char*> names;
+};
+static Profiler g_prof;
+void prof_mark(cudaStream_t s, const char* name) {
+  if (!g_prof.on) return;
+  cudaEvent_t e = nullptr;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, s);
+  g_prof.ev.push_back(e);
+  g_prof.names.push_back(name);
+}
+
+struct Slot {
+  uint8_t* base = nullptr;   // one allocation, fields at 256-byte aligned offsets
+  Inputs in{};
+  cudaEvent_t staged = nullptr;     // H2D of this slot finished (copy stream)
+  cudaEvent_t consumed = nullptr;   // last compute that read this slot finished (compute stream)
+  bool has_data = false;
+};
+
+}  // namespace drl
+
+using namespace drl;
+
+struct drl_learner {
+  drl_learner_config cfg{};
+  int B = 0, T = 0, A = 0, M = 0, Mb = 0;
+  ParamLayout pl{};
+  cudaStream_t compute = nullptr, copy = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done = nullptr;
+  float* params = nullptr;
+  float* ms = nullptr;
+  float* bucket = nullptr;   // [padded_total grads | 4 loss sums]
+  Acts act{};
+  Bwd bwd{};
+  VtraceOut vt{};
+  OptState opt{};
+  long long* d_step = nullptr;
+  float* d_lr = nullptr;
+  float* d_out = nullptr;
+  float* h_out = nullptr;    // pinned [8]
+  float* h_flat = nullptr;   // pinned scratch for set/get params (padded_total floats)
+  std::vector<Slot> slots;
+  std::vector<void*> allocs;
+  bool pending = false;      // a step was enqueued and its scalars not yet collected
+  int launches = 0;
+  // CUDA graphs (one per slot) for forward+backward and for apply
+  std::vector<cudaGraphExec_t> graph_fb;
+  cudaGraphExec_t graph_apply = nullptr;
+};
+
+namespace {
+
+template <class T>
+int dev_alloc(drl_learner* h, T** p, size_t count, int fill_byte = 0) {
+  void* q = nullptr;
+  DRL_CUDA_CHECK(cudaMalloc(&q, count * sizeof(T) + 256));
+  DRL_CUDA_CHECK(cudaMemset(q, fill_byte, count * sizeof(T) + 256));
+  h->allocs.push_back(q);
+  *p = static_cast<T*>(q);
+  return DRL_OK;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int check_handle(const drl_learner* h) {
+  if (!h) { set_error("null learner handle"); return DRL_ERR_INVALID; }
+  return DRL_OK;
+}
+
+int set_device(const drl_learner* h) {
+  DRL_CUDA_CHECK(cudaSetDevice(h->cfg.device));
+  return DRL_OK;
+}
+
+// packed (TF-flat, API) <-> padded (device) copies through the pinned scratch
+int upload_flat(drl_learner* h, float* dev_padded, const float* host_packed, float pad_value) {
+  for (int64_t i = 0; i < h->pl.padded_total; ++i) h->h_flat[i] = pad_value;
+  for (int i = 0; i < ParamLayout::kNumTensors; ++i)
+    memcpy(h->h_flat + h->pl.padded_off[i], host_packed + h->pl.packed_off[i], h->pl.count[i] * sizeof(float));
+  DRL_CUDA_CHECK(cudaMemcpyAsync(dev_padded, h->h_flat, h->pl.padded_total * sizeof(float), cudaMemcpyHostToDevice,
+                                 h->compute));
+  DRL_CUDA_CHECK(cudaStreamSynchronize(h->compute));
+  return DRL_OK;
+}
+int download_flat(drl_learner* h, const float* dev_padded, float* host_packed) {
+  DRL_CUDA_CHECK(cudaMemcpyAsync(h->h_flat, dev_padded, h->pl.padded_total * sizeof(float), cudaMemcpyDeviceToHost,
+                                 h->compute));
+  DRL_CUDA_CHECK(cudaStreamSynchronize(h->compute));
+  for (int i = 0; i < ParamLayout::kNumTensors; ++i)
+    memcpy(host_packed + h->pl.packed_off[i], h->h_flat + h->pl.padded_off[i], h->pl.count[i] * sizeof(float));
+  return DRL_OK;
+}
+
+int enqueue_forward(drl_learner* h, const Inputs& in, int B, int T) {
+  return net_forward(h->compute, h->pl, h->params, in, h->act, B, T);
+}
+
+int enqueue_forward_backward(drl_learner* h, int slot) {
+  const Inputs& in = h->slots[slot].in;
+  DRL_TRY(enqueue_forward(h, in, h->B, h->T));
+  VtraceCfg vc{h->cfg.discount_factor, h->cfg.baseline_loss_coef, h->cfg.entropy_coef, h->cfg.reward_clipping};
+  prof_mark(h->compute, "vtrace_losses");
+  DRL_TRY(vtrace_losses(h->compute, vc, h->act.policy, h->act.value, in, h->vt, h->bwd.dlogits, h->bwd.dv, h->B,
+                        h->T, h->A));
+  DRL_TRY(net_backward(h->compute, h->pl, h->params, h->bucket, in, h->act, h->bwd, h->B, h->T));
+  return DRL_OK;
+}
+
+int enqueue_apply(drl_learner* h) {
+  prof_mark(h->compute, "optimizer(norm+rmsprop)");
+  DRL_TRY(optimizer_apply(h->compute, h->opt));
+  prof_mark(h->compute, "end");
+  DRL_CUDA_CHECK(cudaMemcpyAsync(h->h_out, h->d_out, 8 * sizeof(float), cudaMemcpyDeviceToHost, h->compute));
+  return DRL_OK;
+}
+
+int run_forward_backward(drl_learner* h, int slot) {
+  Slot& sl = h->slots[slot];
+  if (!sl.has_data) { set_error("slot %d has not been staged", slot); return DRL_ERR_STATE; }
+  DRL_CUDA_CHECK(cudaStreamWaitEvent(h->compute, sl.staged, 0));
+  DRL_CUDA_CHECK(cudaEventRecord(h->ev_start, h->compute));
+  if (h->cfg.use_cuda_graph) {
+    if (!h->graph_fb[slot]) {
+      // one eager pass first: sets the per-kernel shared-memory attributes outside of stream capture
+      // (idempotent: every buffer it writes is fully overwritten by the captured pass)
+      DRL_TRY(enqueue_forward_backward(h, slot));
+      cudaGraph_t g = nullptr;
+      DRL_CUDA_CHECK(cudaStreamBeginCapture(h->compute, cudaStreamCaptureModeThreadLocal));
+      int r = enqueue_forward_backward(h, slot);
+      cudaError_t e = cudaStreamEndCapture(h->compute, &g);
+      if (r != DRL_OK) { if (g) cudaGraphDestroy(g); return r; }
+      if (e != cudaSuccess) { set_error("graph capture failed: %s", cudaGetErrorString(e)); return DRL_ERR_CUDA; }
+      DRL_CUDA_CHECK(cudaGraphInstantiate(&h->graph_fb[slot], g, 0));
+      cudaGraphDestroy(g);
+    }
+    DRL_CUDA_CHECK(cudaGraphLaunch(h->graph_fb[slot], h->compute));
+  } else {
+    DRL_TRY(enqueue_forward_backward(h, slot));
+  }
+  DRL_CUDA_CHECK(cudaEventRecord(sl.consumed, h->compute));
+  return DRL_OK;
+}
+
+int run_apply(drl_learner* h) {
+  if (h->cfg.use_cuda_graph) {
+    if (!h->graph_apply) {
+      cudaGraph_t g = nullptr;
+      DRL_CUDA_CHECK(cudaStreamBeginCapture(h->compute, cudaStreamCaptureModeThreadLocal));
+      int r = enqueue_apply(h);
+      cudaError_t e = cudaStreamEndCapture(h->compute, &g);
+      if (r != DRL_OK) { if (g) cudaGraphDestroy(g); return r; }
+      if (e != cudaSuccess) { set_error("graph capture failed: %s", cudaGetErrorString(e)); return DRL_ERR_CUDA; }
+      DRL_CUDA_CHECK(cudaGraphInstantiate(&h->graph_apply, g, 0));
+      cudaGraphDestroy(g);
+    }
+    DRL_CUDA_CHECK(cudaGraphLaunch(h->graph_apply, h->compute));
+  } else {
+    DRL_TRY(enqueue_apply(h));
+  }
+  DRL_CUDA_CHECK(cudaEventRecord(h->ev_stop, h->compute));
+  DRL_CUDA_CHECK(cudaEventRecord(h->ev_done, h->compute));
+  h->pending = true;
+  return DRL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* drl_last_error(void) { return get_error(); }
+const char* drl_version(void) { return "drl_b200 0.1 (sm_100a; FP32-FFMA gather-GEMM path)"; }
+
+int drl_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int drl_learner_create(const drl_learner_config* cfg, drl_learner** out) {
+  if (!cfg || !out) { set_error("null argument"); return DRL_ERR_INVALID; }
+  *out = nullptr;
+  if (cfg->height != Geo::IH || cfg->width != Geo::IW || cfg->channels != Geo::IC) {
+    set_error("only the reference input geometry 84x84x4 is supported (got %dx%dx%d)", cfg->height, cfg->width,
+              cfg->channels);
+    return DRL_ERR_INVALID;
+  }
+  if (cfg->lstm_size != Geo::L) { set_error("only lstm_size 256 is supported (got %d)", cfg->lstm_size); return DRL_ERR_INVALID; }
+  if (cfg->trajectory < 3 || cfg->trajectory > 32) { set_error("trajectory must be in [3,32]"); return DRL_ERR_INVALID; }
+  if (cfg->num_action < 2 || cfg->num_action > 32) { set_error("num_action must be in [2,32]"); return DRL_ERR_INVALID; }
+  if (cfg->batch < 1) { set_error("batch must be >= 1"); return DRL_ERR_INVALID; }
+  if (cfg->reward_clipping != DRL_REWARD_ABS_ONE && cfg->reward_clipping != DRL_REWARD_SOFT_ASYMMETRIC) {
+    set_error("reward_clipping must be DRL_REWARD_ABS_ONE or DRL_REWARD_SOFT_ASYMMETRIC");   // utils.py:45
+    return DRL_ERR_INVALID;
+  }
+  if (cfg->math_mode != 0 && cfg->math_mode != 1) { set_error("math_mode %d not available in this build", cfg->math_mode); return DRL_ERR_INVALID; }
+  if (drl_device_count() <= cfg->device) { set_error("CUDA device %d not available (no CPU fallback)", cfg->device); return DRL_ERR_CUDA; }
+
+  drl_learner* h = new drl_learner();
+  h->cfg = *cfg;
+  if (h->cfg.num_slots < 1) h->cfg.num_slots = 2;
+  h->B = cfg->batch; h->T = cfg->trajectory; h->A = cfg->num_action;
+  h->M = h->B * h->T; h->Mb = h->B * (h->T - 2);
+  h->pl.init(h->A);
+  int rc = [&]() -> int {
+    DRL_TRY(set_device(h));
+    DRL_CUDA_CHECK(cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
+    DRL_CUDA_CHECK(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
+    DRL_CUDA_CHECK(cudaEventCreate(&h->ev_start));
+    DRL_CUDA_CHECK(cudaEventCreate(&h->ev_stop));
+    DRL_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
+    const size_t M = h->M, Mb = h->Mb, A = h->A, NP = h->pl.padded_total;
+    DRL_TRY(dev_alloc(h, &h->params, NP));
+    DRL_TRY(dev_alloc(h, &h->ms, NP));
+    DRL_TRY(dev_alloc(h, &h->bucket, NP + 4));
+    {  // RMSProp slots start at ONE (TF1 RMSPropOptimizer._create_slots)
+      std::vector<float> ones(NP, 1.0f);
+      DRL_CUDA_CHECK(cudaMemcpy(h->ms, ones.data(), NP * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    Acts& a = h->act;
+    DRL_TRY(dev_alloc(h, &a.a1, M * 400 * 32));
+    DRL_TRY(dev_alloc(h, &a.a2, M * 81 * 64));
+    DRL_TRY(dev_alloc(h, &a.a3, M * Geo::FLAT));
+    DRL_TRY(dev_alloc(h, &a.e1, A * Geo::EMB));
+    DRL_TRY(dev_alloc(h, &a.table, A * Geo::EMB));
+    DRL_TRY(dev_alloc(h, &a.zpart, (size_t)kLstmSplits * M * Geo::G4));
+    DRL_TRY(dev_alloc(h, &a.gates, M * Geo::G4));
+    DRL_TRY(dev_alloc(h, &a.c1, M * Geo::L));
+    DRL_TRY(dev_alloc(h, &a.tc1, M * Geo::L));
+    DRL_TRY(dev_alloc(h, &a.h1, M * Geo::L));
+    DRL_TRY(dev_alloc(h, &a.hid1, 2 * M * Geo::HID));
+    DRL_TRY(dev_alloc(h, &a.hid2, 2 * M * Geo::HID));
+    DRL_TRY(dev_alloc(h, &a.logits, M * A));
+    DRL_TRY(dev_alloc(h, &a.policy, M * A));
+    DRL_TRY(dev_alloc(h, &a.value, M));
+    Bwd& b = h->bwd;
+    DRL_TRY(dev_alloc(h, &b.dlogits, Mb * 32));
+    DRL_TRY(dev_alloc(h, &b.dv, Mb * 32));
+    DRL_TRY(dev_alloc(h, &b.dhid2, 2 * Mb * Geo::HID));
+    DRL_TRY(dev_alloc(h, &b.dhid1, 2 * Mb * Geo::HID));
+    DRL_TRY(dev_alloc(h, &b.dh_part, 2 * Mb * Geo::L));
+    DRL_TRY(dev_alloc(h, &b.dz, Mb * Geo::G4));
+    DRL_TRY(dev_alloc(h, &b.da3, Mb * Geo::FLAT));
+    DRL_TRY(dev_alloc(h, &b.du, Mb * Geo::EMB));
+    DRL_TRY(dev_alloc(h, &b.dpre2, A * Geo::EMB));
+    DRL_TRY(dev_alloc(h, &b.dpre1, A * Geo::EMB));
+    DRL_TRY(dev_alloc(h, &b.da2, Mb * 81 * 64));
+    DRL_TRY(dev_alloc(h, &b.da1, Mb * 400 * 32));
+    b.wg_part_floats = wgrad_partial_floats(h->B, h->T);
+    DRL_TRY(dev_alloc(h, &b.wg_part, b.wg_part_floats));
+    VtraceOut& v = h->vt;
+    const size_t nt = (size_t)h->B * (h->T - 2);
+    DRL_TRY(dev_alloc(h, &v.vs, nt));
+    DRL_TRY(dev_alloc(h, &v.clipped_rho, nt));
+    DRL_TRY(dev_alloc(h, &v.vs_plus_1, nt));
+    DRL_TRY(dev_alloc(h, &v.pg_adv, nt));
+    DRL_TRY(dev_alloc(h, &v.loss_partials, (size_t)cdiv(h->B, 4) * 3));
+    DRL_TRY(dev_alloc(h, &v.ticket, 1));
+    v.loss_sums = h->bucket + NP;
+    DRL_TRY(dev_alloc(h, &h->d_step, 1));
+    DRL_TRY(dev_alloc(h, &h->d_lr, 1));
+    DRL_TRY(dev_alloc(h, &h->d_out, 8));
+    DRL_CUDA_CHECK(cudaHostAlloc((void**)&h->h_out, 8 * sizeof(float), cudaHostAllocDefault));
+    DRL_CUDA_CHECK(cudaHostAlloc((void**)&h->h_flat, NP * sizeof(float), cudaHostAllocDefault));
+    memset(h->h_out, 0, 8 * sizeof(float));
+    OptState& o = h->opt;
+    o.params = h->params; o.ms = h->ms; o.grads = h->bucket; o.n = (int64_t)NP;
+    o.nblk = 148 * 4;
+    DRL_TRY(dev_alloc(h, &o.norm_partials, o.nblk));
+    o.step = h->d_step; o.lr_cur = h->d_lr; o.out = h->d_out; o.loss_sums = v.loss_sums;
+    o.start_lr = cfg->start_learning_rate; o.end_lr = cfg->end_learning_rate; o.learning_frame = cfg->learning_frame;
+    o.clip_norm = cfg->gradient_clip_norm; o.baseline_coef = cfg->baseline_loss_coef; o.entropy_coef = cfg->entropy_coef;
+    // staging slots (device), caller's batch-major layout
+    const size_t BT = (size_t)h->B * h->T;
+    h->slots.resize(h->cfg.num_slots);
+    h->graph_fb.assign(h->cfg.num_slots, nullptr);
+    for (Slot& s : h->slots) {
+      size_t off = 0;
+      const size_t o_frames = off; off = align_up(off + BT * Geo::FRAME, 256);
+      const size_t o_rew = off; off = align_up(off + BT * 4, 256);
+      const size_t o_act = off; off = align_up(off + BT * 4, 256);
+      const size_t o_done = off; off = align_up(off + BT, 256);
+      const size_t o_mu = off; off = align_up(off + BT * A * 4, 256);
+      const size_t o_pa = off; off = align_up(off + BT * 4, 256);
+      const size_t o_h = off; off = align_up(off + BT * Geo::L * 4, 256);
+      const size_t o_c = off; off = align_up(off + BT * Geo::L * 4, 256);
+      DRL_TRY(dev_alloc(h, &s.base, off));
+      s.in.frames = s.base + o_frames;
+      s.in.reward = reinterpret_cast<float*>(s.base + o_rew);
+      s.in.action = reinterpret_cast<int32_t*>(s.base + o_act);
+      s.in.done = s.base + o_done;
+      s.in.mu = reinterpret_cast<float*>(s.base + o_mu);
+      s.in.pa = reinterpret_cast<int32_t*>(s.base + o_pa);
+      s.in.h0 = reinterpret_cast<float*>(s.base + o_h);
+      s.in.c0 = reinterpret_cast<float*>(s.base + o_c);
+      DRL_CUDA_CHECK(cudaEventCreateWithFlags(&s.staged, cudaEventDisableTiming));
+      DRL_CUDA_CHECK(cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming));
+    }
+    DRL_CUDA_CHECK(cudaDeviceSynchronize());
+    return DRL_OK;
+  }();
+  if (rc != DRL_OK) {
+    std::string keep = get_error();
+    drl_learner_destroy(h);
+    set_error("%s", keep.c_str());
+    return rc;
+  }
+  *out = h;
+  return DRL_OK;
+}
+
+int drl_learner_destroy(drl_learner* h) {
+  if (!h) return DRL_OK;
+  cudaSetDevice(h->cfg.device);
+  cudaDeviceSynchronize();
+  for (auto g : h->graph_fb) if (g) cudaGraphExecDestroy(g);
+  if (h->graph_apply) cudaGraphExecDestroy(h->graph_apply);
+  for (Slot& s : h->slots) {
+    if (s.staged) cudaEventDestroy(s.staged);
+    if (s.consumed) cudaEventDestroy(s.consumed);
+  }
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->h_out) cudaFreeHost(h->h_out);
+  if (h->h_flat) cudaFreeHost(h->h_flat);
+  if (h->ev_start) cudaEventDestroy(h->ev_start);
+  if (h->ev_stop) cudaEventDestroy(h->ev_stop);
+  if (h->ev_done) cudaEventDestroy(h->ev_done);
+  if (h->compute) cudaStreamDestroy(h->compute);
+  if (h->copy) cudaStreamDestroy(h->copy);
+  cudaGetLastError();
+  delete h;
+  return DRL_OK;
+}
+
+int drl_learner_param_count(const drl_learner* h, int64_t* n) {
+  DRL_TRY(check_handle(h));
+  if (!n) { set_error("null argument"); return DRL_ERR_INVALID; }
+  *n = h->pl.packed_total;
+  return DRL_OK;
+}
+
+int drl_learner_set_params(drl_learner* h, const float* host_flat, int64_t n) {
+  DRL_TRY(check_handle(h));
+  if (!host_flat || n != h->pl.packed_total) { set_error("set_params: expected %lld floats, got %lld", (long long)h->pl.packed_total, (long long)n); return DRL_ERR_INVALID; }
+  DRL_TRY(set_device(h));
+  return upload_flat(h, h->params, host_flat, 0.0f);
+}
+int drl_learner_get_params(drl_learner* h, float* host_flat, int64_t n) {
+  DRL_TRY(check_handle(h));
+  if (!host_flat || n != h->pl.packed_total) { set_error("get_params: expected %lld floats", (long long)h->pl.packed_total); return DRL_ERR_INVALID; }
+  DRL_TRY(set_device(h));
+  return download_flat(h, h->params, host_flat);
+}
+int drl_learner_set_opt_state(drl_learner* h, const float* host_ms_flat, int64_t n, int64_t step) {
+  DRL_TRY(check_handle(h));
+  if (!host_ms_flat || n != h->pl.packed_total) { set_error("set_opt_state: expected %lld floats", (long long)h->pl.packed_total); return DRL_ERR_INVALID; }
+  DRL_TRY(set_device(h));
+  DRL_TRY(upload_flat(h, h->ms, host_ms_flat, 1.0f));
+  long long st = step;
+  DRL_CUDA_CHECK(cudaMemcpy(h->d_step, &st, sizeof(st), cudaMemcpyHostToDevice));
+  return DRL_OK;
+}
+int drl_learner_get_opt_state(drl_learner* h, float* host_ms_flat, int64_t n, int64_t* step) {
+  DRL_TRY(check_handle(h));
+  if (n != h->pl.packed_total) { set_error("get_opt_state: expected %lld floats", (long long)h->pl.packed_total); return DRL_ERR_INVALID; }
+  DRL_TRY(set_device(h));
+  if (host_ms_flat) DRL_TRY(download_flat(h, h->ms, host_ms_flat));
+  if (step) {
+    long long st = 0;
+    DRL_CUDA_CHECK(cudaStreamSynchronize(h->compute));
+    DRL_CUDA_CHECK(cudaMemcpy(&st, h->d_step, sizeof(st), cudaMemcpyDeviceToHost));
+    *step = st;
+  }
+  return DRL_OK;
+}
+int drl_learner_get_grads(drl_learner* h, float* host_flat, int64_t n) {
+  DRL_TRY(check_handle(h));
+  if (!host_flat || n != h->pl.packed_total) { set_error("get_grads: expected %lld floats", (long long)h->pl.packed_total); return DRL_ERR_INVALID; }
+  DRL_TRY(set_device(h));
+  return download_flat(h, h->bucket, host_flat);
+}
+
+int drl_learner_stage(drl_learner* h, int32_t slot, const uint8_t* state, const float* reward, const int32_t* action,
+                      const uint8_t* done, const float* behavior_policy, const int32_t* previous_action,
+                      const float* initial_h, const float* initial_c) {
+  DRL_TRY(check_handle(h));
+  if (slot < 0 || slot >= (int)h->slots.size()) { set_error("slot %d out of range", slot); return DRL_ERR_INVALID; }
+  if (!state || !reward || !action || !done || !behavior_policy || !previous_action || !initial_h || !initial_c) {
+    set_error("stage: null input pointer");
+    return DRL_ERR_INVALID;
+  }
+  DRL_TRY(set_device(h));
+  Slot& s = h->slots[slot];
+  const size_t BT = (size_t)h->B * h->T;
+  // do not overwrite a slot the compute stream is still reading
+  DRL_CUDA_CHECK(cudaStreamWaitEvent(h->copy, s.consumed, 0));
+  auto cp = [&](const void* dst, const void* src, size_t bytes) -> cudaError_t {
+    return cudaMemcpyAsync(const_cast<void*>(dst), src, bytes, cudaMemcpyHostToDevice, h->copy);
+  };
+  DRL_CUDA_CHECK(cp(s.in.frames, state, BT * Geo::FRAME));
+  DRL_CUDA_CHECK(cp(s.in.reward, reward, BT * 4));
+  DRL_CUDA_CHECK(cp(s.in.action, action, BT * 4));
+  DRL_CUDA_CHECK(cp(s.in.done, done, BT));
+  DRL_CUDA_CHECK(cp(s.in.mu, behavior_policy, BT * h->A * 4));
+  DRL_CUDA_CHECK(cp(s.in.pa, previous_action, BT * 4));
+  DRL_CUDA_CHECK(cp(s.in.h0, initial_h, BT * Geo::L * 4));
+  DRL_CUDA_CHECK(cp(s.in.c0, initial_c, BT * Geo::L * 4));
+  DRL_CUDA_CHECK(cudaEventRecord(s.staged, h->copy));
+  s.has_data = true;
+  return DRL_OK;
+}
+
+int drl_learner_forward_backward(drl_learner* h, int32_t slot) {
+  DRL_TRY(check_handle(h));
+  if (slot < 0 || slot >= (int)h->slots.size()) { set_error("slot %d out of range", slot); return DRL_ERR_INVALID; }
+  DRL_TRY(set_device(h));
+  return run_forward_backward(h, slot);
+}
+
+int drl_learner_grad_bucket(drl_learner* h, void** dev_ptr, int64_t* count) {
+  DRL_TRY(check_handle(h));
+  if (dev_ptr) *dev_ptr = h->bucket;
+  if (count) *count = h->pl.padded_total + 4;
+  return DRL_OK;
+}
+
+int drl_learner_apply(drl_learner* h) {
+  DRL_TRY(check_handle(h));
+  DRL_TRY(set_device(h));
+  return run_apply(h);
+}
+
+int drl_learner_stream(drl_learner* h, void** stream) {
+  DRL_TRY(check_handle(h));
+  if (!stream) { set_error("null argument"); return DRL_ERR_INVALID; }
+  *stream = h->compute;
+  return DRL_OK;
+}
+
+int drl_learner_step_async(drl_learner* h, int32_t slot) {
+  DRL_TRY(drl_learner_forward_backward(h, slot));
+  return run_apply(h);
+}
+
+int drl_learner_wait(drl_learner* h, drl_step_out* out) {
+  DRL_TRY(check_handle(h));
+  if (!h->pending) { set_error("wait: no step in flight"); return DRL_ERR_STATE; }
+  DRL_TRY(set_device(h));
+  DRL_CUDA_CHECK(cudaEventSynchronize(h->ev_done));
+  h->pending = false;
+  if (out) {
+    out->pi_loss = h->h_out[0];
+    out->baseline_loss = h->h_out[1];
+    out->entropy = h->h_out[2];
+    out->learning_rate = h->h_out[3];
+    out->grad_norm = h->h_out[4];
+    out->total_loss = h->h_out[5];
+    uint32_t lo, hi;
+    memcpy(&lo, &h->h_out[6], 4);
+    memcpy(&hi, &h->h_out[7], 4);
+    out->step = (int64_t)(((uint64_t)hi << 32) | lo);
+  }
+  return DRL_OK;
+}
+
+int drl_learner_step(drl_learner* h, int32_t slot, drl_step_out* out) {
+  DRL_TRY(drl_learner_step_async(h, slot));
+  return drl_learner_wait(h, out);
+}
+
+int drl_learner_forward(drl_learner* h, int32_t slot, float* policy, float* value) {
+  DRL_TRY(check_handle(h));
+  if (slot < 0 || slot >= (int)h->slots.size()) { set_error("slot %d out of range", slot); return DRL_ERR_INVALID; }
+  DRL_TRY(set_device(h));
+  Slot& s = h->slots[slot];
+  if (!s.has_data) { set_error("slot %d has not been staged", slot); return DRL_ERR_STATE; }
+  DRL_CUDA_CHECK(cudaStreamWaitEvent(h->compute, s.staged, 0));
+  DRL_TRY(enqueue_forward(h, s.in, h->B, h->T));
+  DRL_CUDA_CHECK(cudaEventRecord(s.consumed, h->compute));
+  // time-major device rows -> batch-major host arrays
+  const int B = h->B, T = h->T, A = h->A;
+  std::vector<float> pol((size_t)B * T * A), val((size_t)B * T);
+  DRL_CUDA_CHECK(cudaMemcpyAsync(pol.data(), h->act.policy, pol.size() * 4, cudaMemcpyDeviceToHost, h->compute));
+  DRL_CUDA_CHECK(cudaMemcpyAsync(val.data(), h->act.value, val.size() * 4, cudaMemcpyDeviceToHost, h->compute));
+  DRL_CUDA_CHECK(cudaStreamSynchronize(h->compute));
+  for (int t = 0; t < T; ++t)
+    for (int b = 0; b < B; ++b) {
+      const size_t m = (size_t)t * B + b, s2 = (size_t)b * T + t;
+      if (policy) memcpy(policy + s2 * A, pol.data() + m * A, A * sizeof(float));
+      if (value) value[s2] = val[m];
+    }
+  return DRL_OK;
+}
+
+int drl_learner_taps(drl_learner* h, float* vs, float* clipped_rho, float* vs_plus_1, float* pg_advantage) {
+  DRL_TRY(check_handle(h));
+  DRL_TRY(set_device(h));
+  const size_t n = (size_t)h->B * (h->T - 2) * sizeof(float);
+  DRL_CUDA_CHECK(cudaStreamSynchronize(h->compute));
+  if (vs) DRL_CUDA_CHECK(cudaMemcpy(vs, h->vt.vs, n, cudaMemcpyDeviceToHost));
+  if (clipped_rho) DRL_CUDA_CHECK(cudaMemcpy(clipped_rho, h->vt.clipped_rho, n, cudaMemcpyDeviceToHost));
+  if (vs_plus_1) DRL_CUDA_CHECK(cudaMemcpy(vs_plus_1, h->vt.vs_plus_1, n, cudaMemcpyDeviceToHost));
+  if (pg_advantage) DRL_CUDA_CHECK(cudaMemcpy(pg_advantage, h->vt.pg_adv, n, cudaMemcpyDeviceToHost));
+  return DRL_OK;
+}
+
+int drl_learner_read_buffer(drl_learner* h, const char* name, float* host_dst, int64_t n) {
+  DRL_TRY(check_handle(h));
+  if (!name || !host_dst) { set_error("null argument"); return DRL_ERR_INVALID; }
+  DRL_TRY(set_device(h));
+  const size_t M = h->M, Mb = h->Mb, A = h->A;
+  struct Ent { const char* nm; const float* p; size_t cnt; };
+  const Ent tab[] = {
+      {"a1", h->act.a1, M * 400 * 32}, {"a2", h->act.a2, M * 81 * 64}, {"a3", h->act.a3, M * Geo::FLAT},
+      {"emb", h->act.table, A * Geo::EMB}, {"e1", h->act.e1, A * Geo::EMB},
+      {"gates", h->act.gates, M * Geo::G4}, {"h1", h->act.h1, M * Geo::L}, {"c1", h->act.c1, M * Geo::L},
+      {"hid1", h->act.hid1, 2 * M * Geo::HID}, {"hid2", h->act.hid2, 2 * M * Geo::HID},
+      {"logits", h->act.logits, M * A}, {"policy", h->act.policy, M * A}, {"value", h->act.value, M},
+      {"dlogits", h->bwd.dlogits, Mb * 32}, {"dv", h->bwd.dv, Mb * 32}, {"dhid2", h->bwd.dhid2, 2 * Mb * Geo::HID},
+      {"dhid1", h->bwd.dhid1, 2 * Mb * Geo::HID}, {"dh_part", h->bwd.dh_part, 2 * Mb * Geo::L},
+      {"dz", h->bwd.dz, Mb * Geo::G4}, {"da3", h->bwd.da3, Mb * Geo::FLAT}, {"du", h->bwd.du, Mb * Geo::EMB},
+      {"da2", h->bwd.da2, Mb * 81 * 64}, {"da1", h->bwd.da1, Mb * 400 * 32}};
+  for (const Ent& e : tab) {
+    if (strcmp(e.nm, name) == 0) {
+      if ((size_t)n != e.cnt) { set_error("read_buffer(%s): expected %zu floats, got %lld", name, e.cnt, (long long)n); return DRL_ERR_INVALID; }
+      DRL_CUDA_CHECK(cudaStreamSynchronize(h->compute));
+      DRL_CUDA_CHECK(cudaMemcpy(host_dst, e.p, e.cnt * sizeof(float), cudaMemcpyDeviceToHost));
+      return DRL_OK;
+    }
+  }
+  set_error("read_buffer: unknown buffer '%s'", name);
+  return DRL_ERR_INVALID;
+}
+
+int drl_learner_act(drl_learner* h, int32_t n, const uint8_t* state, const int32_t* previous_action,
+                    const float* h_in, const float* c_in, float* policy, float* h_out, float* c_out) {
+  DRL_TRY(check_handle(h));
+  if (n < 1 || n > h->M) { set_error("act: n must be in [1, %d]", h->M); return DRL_ERR_INVALID; }
+  if (!state || !previous_action || !h_in || !c_in) { set_error("act: null input pointer"); return DRL_ERR_INVALID; }
+  DRL_TRY(set_device(h));
+  // reuse staging slot 0 as an [n, 1] batch (B = n, T = 1 makes the time-major/batch-major remap the identity)
+  Slot& s = h->slots[0];
+  DRL_CUDA_CHECK(cudaStreamSynchronize(h->compute));
+  DRL_CUDA_CHECK(cudaStreamSynchronize(h->copy));
+  auto cp = [&](const void* dst, const void* src, size_t bytes) -> cudaError_t {
+    return cudaMemcpyAsync(const_cast<void*>(dst), src, bytes, cudaMemcpyHostToDevice, h->compute);
+  };
+  DRL_CUDA_CHECK(cp(s.in.frames, state, (size_t)n * Geo::FRAME));
+  DRL_CUDA_CHECK(cp(s.in.pa, previous_action, (size_t)n * 4));
+  DRL_CUDA_CHECK(cp(s.in.h0, h_in, (size_t)n * Geo::L * 4));
+  DRL_CUDA_CHECK(cp(s.in.c0, c_in, (size_t)n * Geo::L * 4));
+  s.has_data = false;   // the slot no longer holds a training batch
+  DRL_TRY(enqueue_forward(h, s.in, n, 1));
+  if (policy) DRL_CUDA_CHECK(cudaMemcpyAsync(policy, h->act.policy, (size_t)n * h->A * 4, cudaMemcpyDeviceToHost, h->compute));
+  if (h_out) DRL_CUDA_CHECK(cudaMemcpyAsync(h_out, h->act.h1, (size_t)n * Geo::L * 4, cudaMemcpyDeviceToHost, h->compute));
+  if (c_out) DRL_CUDA_CHECK(cudaMemcpyAsync(c_out, h->act.c1, (size_t)n * Geo::L * 4, cudaMemcpyDeviceToHost, h->compute));
+  DRL_CUDA_CHECK(cudaStreamSynchronize(h->compute));
+  return DRL_OK;
+}
+
+int drl_learner_profile_step(drl_learner* h, int32_t slot, char* names, int64_t names_len, float* ms,
+                             int32_t max_kernels, int32_t* count) {
+  DRL_TRY(check_handle(h));
+  if (slot < 0 || slot >= (int)h->slots.size()) { set_error("slot %d out of range", slot); return DRL_ERR_INVALID; }
+  if (!names || !ms || !count) { set_error("null argument"); return DRL_ERR_INVALID; }
+  DRL_TRY(set_device(h));
+  Slot& sl = h->slots[slot];
+  if (!sl.has_data) { set_error("slot %d has not been staged", slot); return DRL_ERR_STATE; }
+  DRL_CUDA_CHECK(cudaStreamWaitEvent(h->compute, sl.staged, 0));
+  DRL_CUDA_CHECK(cudaStreamSynchronize(h->compute));
+  g_prof.on = true;
+  g_prof.ev.clear();
+  g_prof.names.clear();
+  int rc = enqueue_forward_backward(h, slot);
+  if (rc == DRL_OK) rc = enqueue_apply(h);
+  g_prof.on = false;
+  cudaError_t e = cudaStreamSynchronize(h->compute);
+  int n = 0;
+  std::string joined;
+  if (rc == DRL_OK && e == cudaSuccess) {
+    for (size_t i = 0; i + 1 < g_prof.ev.size() && n < max_kernels; ++i) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, g_prof.ev[i], g_prof.ev[i + 1]);
+      ms[n++] = t;
+      if (!joined.empty()) joined += "\n";
+      joined += g_prof.names[i];
+    }
+  }
+  for (cudaEvent_t ev : g_prof.ev) cudaEventDestroy(ev);
+  g_prof.ev.clear();
+  g_prof.names.clear();
+  if (rc != DRL_OK) return rc;
+  if (e != cudaSuccess) { set_error("profile step failed: %s", cudaGetErrorString(e)); return DRL_ERR_CUDA; }
+  if ((int64_t)joined.size() + 1 > names_len) { set_error("profile: names buffer too small"); return DRL_ERR_INVALID; }
+  memcpy(names, joined.c_str(), joined.size() + 1);
+  *count = n;
+  h->pending = false;
+  return DRL_OK;
+}
+
+int drl_learner_last_step_ms(drl_learner* h, float* ms) {
+  DRL_TRY(check_handle(h));
+  if (!ms) { set_error("null argument"); return DRL_ERR_INVALID; }
+  DRL_TRY(set_device(h));
+  DRL_CUDA_CHECK(cudaEventSynchronize(h->ev_stop));
+  DRL_CUDA_CHECK(cudaEventElapsedTime(ms, h->ev_start, h->ev_stop));
+  return DRL_OK;
+}
+
+int drl_learner_launches_per_step(const drl_learner* h, int32_t* n) {
+  DRL_TRY(check_handle(h));
+  if (!n) { set_error("null argument"); return DRL_ERR_INVALID; }
+  // forward + V-trace/loss kernel + backward + 2 optimizer kernels (valid after the first step)
+  *n = forward_launch_count() + 1 + backward_launch_count() + 2;
+  return DRL_OK;
+}
+
+}  // extern "C"

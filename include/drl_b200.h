@@ -1,0 +1,236 @@
+/*
+ * drl_b200.h -- C-ABI of the B200-native IMPALA learner hot path.
+ *
+ * The reference (chagmgang/distributed_reinforcement_learning @ 1890ce4) has no FFI: its hot
+ * path is a Python call surface over a TF1 graph.  This header is what a replacement of that
+ * path binds (ctypes today).  Every entry point names the reference
+ * interface it replaces (file:line under /root/reference).
+ *
+ * Conventions: extern "C"; plain pointers and sizes; every function returns int
+ * (0 = ok, <0 = error, text via drl_last_error()); no exception crosses the boundary;
+ * pointers are caller-owned unless produced by a *_create; a handle is used by one host
+ * thread at a time (the ring is the exception: it is multi-producer / single-consumer safe).
+ * "host" pointers are CPU memory (pinned or pageable), "dev" pointers are CUDA device memory.
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails with
+ * DRL_ERR_CUDA.
+ */
+#ifndef DRL_B200_H_
+#define DRL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRL_OK 0
+#define DRL_ERR_INVALID (-1) /* bad argument / unsupported configuration */
+#define DRL_ERR_CUDA (-2)    /* CUDA runtime error (text in drl_last_error) */
+#define DRL_ERR_STATE (-3)   /* call out of order (e.g. step before stage) */
+#define DRL_ERR_TIMEOUT (-4) /* ring wait timed out */
+
+#define DRL_REWARD_ABS_ONE 0         /* agent/impala.py:45-46 */
+#define DRL_REWARD_SOFT_ASYMMETRIC 1 /* agent/impala.py:47-49 */
+
+/* Last error text of the calling thread ("" if none). */
+const char* drl_last_error(void);
+/* Library version string, e.g. "drl_b200 0.1 sm_100a". */
+const char* drl_version(void);
+/* Number of CUDA devices visible (0 when there is none / no driver). */
+int drl_device_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Learner: replaces impala.Agent's learner graph + Agent.train (agent/impala.py:11-103,132-148)
+ * over model/impala_actor_critic.py:33-118 and optimizer/vtrace.py:29-126.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct drl_learner drl_learner;
+
+typedef struct drl_learner_config {
+  int32_t batch;              /* B trajectories per step on THIS device (config.json:130)      */
+  int32_t trajectory;         /* T, 3..32 (config.json:136)                                      */
+  int32_t height, width, channels; /* 84,84,4 -- only this geometry is supported (config.json:133) */
+  int32_t num_action;         /* A, 2..32 (config.json:134)                                     */
+  int32_t lstm_size;          /* 256 -- only this size is supported (config.json:137)           */
+  float discount_factor;      /* agent/impala.py:51                                             */
+  float start_learning_rate;  /* agent/impala.py:96                                             */
+  float end_learning_rate;
+  double learning_frame;      /* decay_steps of tf.train.polynomial_decay                       */
+  float baseline_loss_coef;   /* agent/impala.py:93                                             */
+  float entropy_coef;
+  float gradient_clip_norm;   /* agent/impala.py:98                                             */
+  int32_t reward_clipping;    /* DRL_REWARD_*                                                   */
+  int32_t device;             /* CUDA device ordinal                                            */
+  int32_t num_slots;          /* device staging slots for stream-overlapped H2D (>=1, default 2) */
+  int32_t use_cuda_graph;     /* 1: capture forward+backward(+apply) into CUDA graphs           */
+  int32_t math_mode;          /* 0 = default for this build; 1 = FP32 FFMA; 2 = tcgen05 3xTF32  */
+} drl_learner_config;
+
+/* Results of one step: the 4 floats Agent.train returns (agent/impala.py:144-148) + grad norm. */
+typedef struct drl_step_out {
+  float pi_loss;
+  float baseline_loss;
+  float entropy;
+  float learning_rate;
+  float grad_norm;   /* global norm before clipping (tf.clip_by_global_norm's second output) */
+  float total_loss;  /* agent/impala.py:93 */
+  int64_t step;      /* global_step AFTER this update (agent/impala.py:95,100) */
+} drl_step_out;
+
+/* impala.Agent.__init__ (agent/impala.py:11-103): allocates parameters (zeros), RMSProp slots
+ * (ones, TF1 semantics), activations, staging slots, streams and events on cfg->device. */
+int drl_learner_create(const drl_learner_config* cfg, drl_learner** out);
+int drl_learner_destroy(drl_learner* h);
+
+/* Number of learnable floats (4,153,267 for the reference geometry). */
+int drl_learner_param_count(const drl_learner* h, int64_t* n);
+/* Flat float32 parameter vector in TF layouts / TF variable-creation order
+ * (conv HWIO, dense [in,out], LSTM [in+h, 4*units] gate order i,j,f,o); replaces
+ * global_variables_initializer / Saver.restore (agent/impala.py:105-109,114-116). */
+int drl_learner_set_params(drl_learner* h, const float* host_flat, int64_t n);
+int drl_learner_get_params(drl_learner* h, float* host_flat, int64_t n);      /* parameter_sync / Saver.save */
+/* RMSProp "ms" slots (same flat layout) and global_step -- optimizer state of agent/impala.py:95-100. */
+int drl_learner_set_opt_state(drl_learner* h, const float* host_ms_flat, int64_t n, int64_t step);
+int drl_learner_get_opt_state(drl_learner* h, float* host_ms_flat, int64_t n, int64_t* step);
+/* Gradient of total_loss (before clipping; summed over ranks if an all-reduce ran) -- parity tap
+ * for optimizer.compute_gradients (agent/impala.py:98). */
+int drl_learner_get_grads(drl_learner* h, float* host_flat, int64_t n);
+
+/* Feed of Agent.train (agent/impala.py:134-142): asynchronous H2D of one batch-major batch
+ * into device staging slot `slot` on the copy stream.  state u8 [B,T,H,W,C]; reward f32 [B,T];
+ * action i32 [B,T]; done u8/bool [B,T]; behavior_policy f32 [B,T,A]; previous_action i32 [B,T];
+ * initial_h, initial_c f32 [B,T,L].  The /255 normalisation (agent/impala.py:133) happens on
+ * the device.  Host buffers must stay valid until the next drl_learner_wait / _step on the slot. */
+int drl_learner_stage(drl_learner* h, int32_t slot,
+                      const uint8_t* state, const float* reward, const int32_t* action,
+                      const uint8_t* done, const float* behavior_policy,
+                      const int32_t* previous_action, const float* initial_h, const float* initial_c);
+
+/* sess.run([pi_loss, baseline_loss, entropy, learning_rate, train_op]) (agent/impala.py:144-146):
+ * forward, V-trace, losses, backward, global-norm clip, RMSProp, step += 1 on slot `slot`;
+ * blocks until the scalars are on the host. */
+int drl_learner_step(drl_learner* h, int32_t slot, drl_step_out* out);
+/* Same, asynchronous: enqueue on the compute stream; drl_learner_wait collects the scalars. */
+int drl_learner_step_async(drl_learner* h, int32_t slot);
+int drl_learner_wait(drl_learner* h, drl_step_out* out);
+
+/* Data-parallel split of the step: forward+backward leaves the local gradient
+ * sum in the bucket; the caller all-reduces (SUM) `count` floats at `dev_ptr` across ranks on
+ * `stream` (the bucket tail carries the 3 loss sums so one collective covers them); apply does
+ * clip + RMSProp on the reduced bucket. */
+int drl_learner_forward_backward(drl_learner* h, int32_t slot);
+int drl_learner_grad_bucket(drl_learner* h, void** dev_ptr, int64_t* count);
+int drl_learner_apply(drl_learner* h);          /* async; follow with drl_learner_wait */
+/* The handle's compute stream (cudaStream_t as void*), for ordering external work (NCCL). */
+int drl_learner_stream(drl_learner* h, void** stream);
+
+/* Forward only (no update): the learner-side values of build_network
+ * (model/impala_actor_critic.py:71-118): policy [B,T,A] and value [B,T], batch-major, for all T
+ * rows (first/middle/last are the slices [:, :-2], [:, 1:-1], [:, 2:]).  Host outputs. */
+int drl_learner_forward(drl_learner* h, int32_t slot, float* policy, float* value);
+
+/* Parity taps of the last step (agent/impala.py:68-80): vs, clipped_rho, vs_plus_1, pg_advantage,
+ * each host float32 [B, T-2] batch-major.  NULL pointers are skipped. */
+int drl_learner_taps(drl_learner* h, float* vs, float* clipped_rho, float* vs_plus_1, float* pg_advantage);
+
+/* Debug/parity read of an internal activation by name into host memory (float32, device layout:
+ * rows are TIME-MAJOR m = t*B + b).  Names: "a1" [M,20,20,32], "a2" [M,9,9,64], "a3" [M,3136],
+ * "emb" [A,256], "h1","c1" [M,256], "logits","policy" [M,A], "value" [M].  n = element count. */
+int drl_learner_read_buffer(drl_learner* h, const char* name, float* host_dst, int64_t n);
+
+/* Actor-side shim of Agent.get_policy_and_action (agent/impala.py:118-130): n independent
+ * single-step forwards.  state u8 [n,H,W,C]; previous_action i32 [n]; h,c f32 [n,L] ->
+ * policy [n,A], h_out, c_out [n,L] (host).  n <= batch*trajectory. */
+int drl_learner_act(drl_learner* h, int32_t n, const uint8_t* state, const int32_t* previous_action,
+                    const float* h_in, const float* c_in, float* policy, float* h_out, float* c_out);
+
+/* Measurement aid (bench.py roofline): runs ONE real step on a staged slot with a CUDA event recorded
+ * on the compute stream before every kernel launch and returns per-launch device times.  names is a
+ * '\n'-joined list (names_len bytes available), ms[i] the time from launch i to launch i+1. */
+int drl_learner_profile_step(drl_learner* h, int32_t slot, char* names, int64_t names_len, float* ms,
+                             int32_t max_kernels, int32_t* count);
+/* Device-time of the last step's compute (CUDA events on the compute stream), milliseconds. */
+int drl_learner_last_step_ms(drl_learner* h, float* ms);
+/* Number of kernel launches one step issues (for bench.py's gpu_launches claim). */
+int drl_learner_launches_per_step(const drl_learner* h, int32_t* n);
+
+/* ------------------------------------------------------------------------------------------
+ * Stand-alone V-trace (optimizer/vtrace.py), host-pointer convenience forms + device forms.
+ * ------------------------------------------------------------------------------------------ */
+/* vtrace.from_importance_weights (optimizer/vtrace.py:71-103): time-major [T,B] float32 inputs,
+ * bootstrap_value [B]; outputs vs, clipped_rhos [T,B].  clip_rho_threshold < 0 means None. */
+int drl_vtrace_from_importance_weights(const float* log_rhos, const float* discounts,
+                                       const float* rewards, const float* values,
+                                       const float* bootstrap_value, int32_t T, int32_t B,
+                                       float clip_rho_threshold, float* vs, float* clipped_rhos);
+int drl_vtrace_from_importance_weights_dev(const float* log_rhos, const float* discounts,
+                                           const float* rewards, const float* values,
+                                           const float* bootstrap_value, int32_t T, int32_t B,
+                                           float clip_rho_threshold, float* vs, float* clipped_rhos,
+                                           void* stream);
+/* vtrace.from_softmax (optimizer/vtrace.py:29-69): batch-major behavior/target softmax [B,T,A],
+ * actions i32 [B,T], discounts/rewards/values/next_values f32 [B,T] -> vs, clipped_rho [B,T]. */
+int drl_vtrace_from_softmax(const float* behavior_policy_softmax, const float* target_policy_softmax,
+                            const int32_t* actions, const float* discounts, const float* rewards,
+                            const float* values, const float* next_values, int32_t B, int32_t T,
+                            int32_t A, float clip_rho_threshold, float* vs, float* clipped_rho);
+int drl_vtrace_from_softmax_dev(const float* behavior_policy_softmax, const float* target_policy_softmax,
+                                const int32_t* actions, const float* discounts, const float* rewards,
+                                const float* values, const float* next_values, int32_t B, int32_t T,
+                                int32_t A, float clip_rho_threshold, float* vs, float* clipped_rho,
+                                void* stream);
+
+/* The three loss sums of optimizer/vtrace.py:105-126 and log_probs_from_softmax_and_actions (:16-27)
+ * in one pass over host arrays: softmax [B,T,A], actions i32 [B,T], advantages/vs/value f32 [B,T] ->
+ * sums[3] = { -sum log(pi(a)+1e-8)*adv, 0.5*sum (vs-value)^2, sum pi*log(pi) }, log_probs [B,T]
+ * (= log pi(a), no epsilon; may be NULL). */
+int drl_vtrace_loss_sums(const float* softmax, const int32_t* actions, const float* advantages,
+                         const float* vs, const float* value, int32_t B, int32_t T, int32_t A,
+                         float* sums, float* log_probs);
+
+/* ------------------------------------------------------------------------------------------
+ * Trajectory ring: replaces buffer_queue.FIFOQueue (distributed_queue/buffer_queue.py:418-512).
+ * A FIFO of `capacity` trajectories kept in pinned host memory, organised as batch slots of
+ * `batch` trajectories in field-major order so that a popped batch is 8 contiguous [B, ...]
+ * arrays ready for one async H2D each.  next_state is accepted by the Python shim and dropped
+ * (the learner never reads it, train_impala.py:100-108).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct drl_ring drl_ring;
+
+typedef struct drl_ring_batch {      /* views into the ring's pinned memory, valid until release */
+  uint8_t* state;            /* [B,T,H,W,C] */
+  float* reward;             /* [B,T]       */
+  uint8_t* done;             /* [B,T]       */
+  float* behavior_policy;    /* [B,T,A]     */
+  int32_t* action;           /* [B,T]       */
+  int32_t* previous_action;  /* [B,T]       */
+  float* previous_h;         /* [B,T,L]     */
+  float* previous_c;         /* [B,T,L]     */
+  int32_t slot;              /* batch-slot index to pass to drl_ring_release */
+} drl_ring_batch;
+
+/* FIFOQueue.__init__ (buffer_queue.py:419-466).  capacity is rounded up to a multiple of batch
+ * (+ one extra batch slot so producers can fill while the consumer holds one).  pinned=1 uses
+ * cudaHostAlloc; if that fails (no device) it falls back to page-aligned malloc and *pinned=0. */
+int drl_ring_create(int32_t trajectory, int32_t height, int32_t width, int32_t channels,
+                    int32_t num_action, int32_t lstm_size, int32_t capacity, int32_t batch,
+                    int32_t want_pinned, drl_ring** out);
+int drl_ring_destroy(drl_ring* r);
+int drl_ring_is_pinned(const drl_ring* r);
+/* FIFOQueue.append_to_queue (buffer_queue.py:468-484): copies one trajectory in; blocks while the
+ * ring is full (timeout_ms < 0: forever; DRL_ERR_TIMEOUT otherwise). */
+int drl_ring_push(drl_ring* r, const uint8_t* state, const float* reward, const uint8_t* done,
+                  const float* behavior_policy, const int32_t* action, const int32_t* previous_action,
+                  const float* previous_h, const float* previous_c, int32_t timeout_ms);
+/* FIFOQueue.sample_batch (buffer_queue.py:486-505): pops the oldest `batch` trajectories (FIFO
+ * order) as one batch slot; blocks until a full batch is available. */
+int drl_ring_pop_batch(drl_ring* r, drl_ring_batch* out, int32_t timeout_ms);
+/* Hands a popped batch slot back to the producers. */
+int drl_ring_release(drl_ring* r, int32_t slot);
+/* FIFOQueue.get_size (buffer_queue.py:507-509): trajectories enqueued and not yet popped. */
+int drl_ring_size(drl_ring* r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRL_B200_H_ */

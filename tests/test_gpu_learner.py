@@ -1,0 +1,172 @@
+"""-m gpu: the CUDA learner step through the C-ABI against the float64 CPU oracle on identical seeded
+synthetic trajectories: activations, V-trace taps, the three losses, EVERY
+parameter gradient, and the parameters / RMSProp slots after the update.  Bar: 1e-4 relative fp32
+(BASELINE.json north_star), metric in tests/parity.py."""
+import numpy as np
+import pytest
+import torch
+
+import parity
+from oracle import impala_torch as it
+from oracle import synthetic
+
+pytestmark = pytest.mark.gpu
+
+
+def _assert_all(errs, tol=parity.TOL, update_tol=1e-3):
+    bad = {k: v for k, v in errs.items()
+           if v > (update_tol if k.startswith("update/") else tol) and not k.startswith("lr")}
+    assert not bad, "parity failures (rel err): %s" % sorted(bad.items(), key=lambda kv: -kv[1])[:12]
+    for k, v in errs.items():
+        if k.startswith("lr"):
+            assert v < 1e-9, (k, v)
+
+
+def test_step_small_config(native):
+    """BASELINE config 1 shape: B=4, T=20."""
+    _assert_all(parity.compare_step(4, T=20))
+
+
+def test_step_reference_config(native):
+    """BASELINE config 2 shape: B=32, T=20 (the bench workload)."""
+    _assert_all(parity.compare_step(32, T=20, layers=False))
+
+
+@pytest.mark.parametrize("B,T,A", [(1, 3, 2), (2, 5, 18), (3, 7, 6), (5, 32, 18), (1, 20, 31)])
+def test_step_ragged_shapes(native, B, T, A):
+    """Odd batch sizes (rows not a multiple of any tile), minimum / maximum trajectory, other action counts."""
+    _assert_all(parity.compare_step(B, T=T, A=A))
+
+
+def test_three_steps_track_oracle(native):
+    """Three updates on the same batch: losses/lr/grad-norm of every step and the final parameters and
+    RMSProp slots (ms0 = 1, eps inside sqrt, global-norm clip, step counter) follow the oracle."""
+    _assert_all(parity.compare_step(4, T=20, steps=3, layers=False))
+
+
+def test_soft_asymmetric_reward_clipping(native):
+    _assert_all(parity.compare_step(3, T=9, reward_clipping="soft_asymmetric", layers=False))
+
+
+def test_cuda_graph_path_matches(native):
+    _assert_all(parity.compare_step(4, T=20, steps=2, layers=False, use_cuda_graph=True))
+
+
+def test_matches_golden_fixture(native):
+    """The committed golden vectors (tests/golden/impala_step_B2_T6.npz, made by make_golden.py)."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "impala_step_B2_T6.npz"))
+    B, T, A = int(z["B"]), int(z["T"]), int(z["A"])
+    batch, params, cfg = parity.make_case(B, T, A, seed=int(z["seed"]))
+    eng = parity.native_learner(batch, params, cfg)
+    try:
+        eng.stage(0, *[batch[k] for k in synthetic.TRAIN_FIELDS])
+        out = eng.step(0)
+        taps = eng.taps()
+        g = eng.get_grads()
+    finally:
+        eng.close()
+    for k in ("pi_loss", "baseline_loss", "entropy"):
+        assert abs(out[k] - float(z[k])) <= parity.TOL * max(abs(float(z[k])), 1e-30), k
+    for k in ("vs", "clipped_rho", "vs_plus_1", "pg_advantage"):
+        assert parity.rel_err(taps[k], z[k]) < parity.TOL, k
+    gd = it.unflatten_params(g, torch.float64, num_action=A)
+    for n in gd:
+        got = gd[n].numpy()
+        if "grad_" + n in z:
+            assert parity.rel_err(got, z["grad_" + n]) < parity.TOL, n
+        else:       # big tensors are stored as a strided sample + l2 norm
+            assert parity.rel_err(got.ravel()[::61], z["gradsample_" + n]) < parity.TOL, n
+            assert abs(np.sqrt(np.sum(got ** 2)) / float(z["gradl2_" + n]) - 1) < parity.TOL, n
+
+
+def test_forward_windows_and_shift_identity(native):
+    """build_network's first/middle/last outputs are slices of one forward (App. C.4) and match the oracle's
+    REFERENCE-SHAPED graph (3 x (T-2) per-timestep network copies)."""
+    B, T, A = 2, 6, 18
+    batch, params, cfg = parity.make_case(B, T, A, seed=99)
+    eng = parity.native_learner(batch, params, cfg)
+    try:
+        eng.stage(0, *[batch[k] for k in synthetic.TRAIN_FIELDS])
+        pol, val = eng.forward(0)
+    finally:
+        eng.close()
+    L = it.Learner(params, torch.float64, "reference", **cfg)
+    o = L.losses(*[batch[k] for k in synthetic.TRAIN_FIELDS])
+    assert parity.rel_err(pol[:, :-2], o["first_policy"].detach().numpy()) < parity.TOL
+    assert parity.rel_err(pol[:, 1:-1], o["middle_policy"].detach().numpy()) < parity.TOL
+    assert parity.rel_err(pol[:, 2:], o["last_policy"].detach().numpy()) < parity.TOL
+    assert parity.rel_err(val[:, :-2], o["first_value"].detach().numpy()) < parity.TOL
+    assert parity.rel_err(val[:, 2:], o["last_value"].detach().numpy()) < parity.TOL
+
+
+def test_act_matches_single_step_network(native):
+    """get_policy_and_action's forward (agent/impala.py:118-130) == network() on single frames."""
+    n, A = 5, 18
+    batch, params, cfg = parity.make_case(n, 3, A, seed=5)
+    eng = parity.native_learner(batch, params, cfg)
+    try:
+        pol, h, c = eng.act(batch["state"][:, 0], batch["previous_action"][:, 0], batch["initial_h"][:, 0],
+                            batch["initial_c"][:, 0])
+    finally:
+        eng.close()
+    p64 = {k: v.double() for k, v in params.items()}
+    x = torch.from_numpy((batch["state"][:, 0].astype(np.float64) / 255).astype(np.float32)).double()
+    a, v, cc, hh = it.network(p64, x, torch.from_numpy(batch["previous_action"][:, 0].astype(np.int64)),
+                              torch.from_numpy(batch["initial_h"][:, 0]).double(),
+                              torch.from_numpy(batch["initial_c"][:, 0]).double(), A, 256)
+    assert parity.rel_err(pol, a.numpy()) < parity.TOL
+    assert parity.rel_err(h, hh.numpy()) < parity.TOL
+    assert parity.rel_err(c, cc.numpy()) < parity.TOL
+
+
+def test_data_parallel_shards_sum_to_full_batch(native):
+    """sum over shards of local gradient buckets == gradient of the global batch (losses are
+    batch SUMS), so one all-reduce(SUM) reproduces the reference update.  Emulated on one GPU: two B=2
+    replicas, buckets added on the host, compared with a B=4 replica and with the oracle."""
+    B, T, A = 4, 8, 18
+    batch, params, cfg = parity.make_case(B, T, A, seed=21)
+    fields = synthetic.TRAIN_FIELDS
+    full = parity.native_learner(batch, params, cfg)
+    try:
+        full.stage(0, *[batch[k] for k in fields])
+        full.forward_backward(0)
+        g_full = full.get_grads()
+    finally:
+        full.close()
+    g_sum = 0
+    for lo, hi in ((0, 2), (2, 4)):
+        sh = synthetic.slice_batch(batch, lo, hi)
+        eng = parity.native_learner(sh, params, cfg)
+        try:
+            eng.stage(0, *[sh[k] for k in fields])
+            eng.forward_backward(0)
+            g_sum = g_sum + eng.get_grads().astype(np.float64)
+        finally:
+            eng.close()
+    assert parity.rel_err(g_sum, g_full) < parity.TOL
+    L = it.Learner(params, torch.float64, "dedup", **cfg)
+    _, g = L.gradients(*[batch[k] for k in fields])
+    assert parity.rel_err(g_sum, it.flatten_grads(g)) < parity.TOL
+
+
+def test_errors_are_loud(native):
+    from distributed_reinforcement_learning_b200 import _native as N
+    from distributed_reinforcement_learning_b200.learner import NativeLearner
+    with pytest.raises(N.DrlError):
+        NativeLearner(batch=2, trajectory=20, input_shape=(64, 64, 4))       # unsupported geometry
+    with pytest.raises(N.DrlError):
+        NativeLearner(batch=2, trajectory=2)                                  # T-2 must be >= 1
+    with pytest.raises(ValueError):
+        NativeLearner(batch=2, reward_clipping="nope")
+    eng = NativeLearner(batch=2, trajectory=5)
+    try:
+        with pytest.raises(N.DrlError):
+            eng.step(0)                                                       # nothing staged
+        with pytest.raises(ValueError):
+            eng.set_params(np.zeros(10, np.float32))
+        b = synthetic.make_batch(3, T=5)
+        with pytest.raises(ValueError):
+            eng.stage(0, *[b[k] for k in synthetic.TRAIN_FIELDS])            # wrong batch size
+    finally:
+        eng.close()
