@@ -75,7 +75,7 @@ def compare_step(B, T=20, A=18, seed=1234, steps=1, reward_clipping="abs_one", l
             o = rec["out"]
             for k, ok in (("pi_loss", "pi_loss"), ("baseline_loss", "baseline_loss"), ("entropy", "entropy"),
                           ("total_loss", "total_loss")):
-                errs["loss/" + k + tag] = rel_err(out[k], float(o[ok]))
+                errs["loss/" + k + tag] = rel_err(out[k], float(o[ok].detach()))
             errs["lr" + tag] = abs(out["learning_rate"] - rec["res"][3])
             errs["grad_norm" + tag] = rel_err(out["grad_norm"], rec["grad_norm"])
             if out["step"] != s + 1:
@@ -108,9 +108,12 @@ def compare_step(B, T=20, A=18, seed=1234, steps=1, reward_clipping="abs_one", l
         md = it.unflatten_params(ms, torch.float64, num_action=A)
         for n in L.params:
             errs["param/" + n] = rel_err(pd[n].numpy(), L.params[n].detach().numpy())
+            # the applied update w_after - w_before, judged against its own size plus the float32 storage
+            # granularity of the parameter it is added to (the GPU stores w in float32, the oracle in float64)
             p0 = params[n].double().numpy()
-            if not n.endswith(".b") or True:
-                errs["update/" + n] = rel_err(pd[n].numpy() - p0, L.params[n].detach().numpy() - p0)
+            du_got, du_exp = pd[n].numpy() - p0, L.params[n].detach().numpy() - p0
+            floor = 4.0 * np.finfo(np.float32).eps * max(np.max(np.abs(p0)), 1e-30) / TOL
+            errs["update/" + n] = float(np.max(np.abs(du_got - du_exp)) / (np.max(np.abs(du_exp)) + floor))
             errs["ms/" + n] = rel_err(md[n].numpy(), L.ms[n].detach().numpy())
         if st != steps:
             errs["opt_step"] = float("inf")

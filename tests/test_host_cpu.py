@@ -1,0 +1,221 @@
+"""CPU (no GPU needed): the C-ABI library loads and exports every symbol include/drl_b200.h declares, compute
+entry points fail LOUDLY without a device (no CPU fallback), the trajectory ring (FIFOQueue replacement) keeps
+FIFO order / blocks / wraps, the host-side parameter inventory agrees with the oracle's, and the product
+package never imports the oracle."""
+import ctypes as C
+import os
+import re
+import threading
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(native):
+    with open(os.path.join(ROOT, "include", "drl_b200.h")) as f:
+        declared = sorted(set(re.findall(r"\b(drl_[a-z0-9_]+)\s*\(", f.read())))
+    assert len(declared) >= 35
+    missing = [n for n in declared if not hasattr(native.lib, n)]
+    assert not missing, missing
+    assert set(native.EXPORTS) == set(declared), set(native.EXPORTS) ^ set(declared)
+    assert b"sm_100a" in native.lib.drl_version()
+
+
+def test_built_for_sm_100a_only(native):
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", native.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_compute_fails_loudly_without_a_device(native):
+    if native.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    from distributed_reinforcement_learning_b200.learner import NativeLearner
+    with pytest.raises(native.DrlError) as ei:
+        NativeLearner(batch=2, trajectory=5)
+    assert "no CPU fallback" in str(ei.value)
+    from distributed_reinforcement_learning_b200.optimizer import vtrace
+    z = np.zeros((3, 2), np.float32)
+    with pytest.raises(native.DrlError):
+        vtrace.from_importance_weights(z, z, z, z, np.zeros(2, np.float32))
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "distributed_reinforcement_learning_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                with open(os.path.join(dp, f)) as fh:
+                    src = fh.read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), os.path.join(dp, f)
+
+
+def test_param_inventory_matches_oracle(native):
+    from distributed_reinforcement_learning_b200.model import impala_actor_critic as m
+    from oracle import impala_torch as it
+    assert m.param_specs() == it.param_specs()
+    assert m.param_specs(num_action=6) == it.param_specs(num_action=6)
+    assert m.param_count() == 4153267
+    flat = m.init_params(seed=3)
+    assert flat.dtype == np.float32 and flat.size == 4153267
+    parts = m.split_flat(flat)
+    assert parts["lstm.w"].shape == (3648, 1024) and float(np.abs(parts["conv2.b"]).max()) == 0.0
+    lim = np.sqrt(6.0 / (8 * 8 * 4 + 8 * 8 * 32))
+    assert np.abs(parts["conv1.w"]).max() <= lim and np.abs(parts["conv1.w"]).max() > 0.9 * lim
+
+
+def test_check_properties(native):
+    from distributed_reinforcement_learning_b200 import utils
+    good = dict(num_actors=2, available_action=[18, 6], env=["a", "b"], model_output=18, reward_clipping="abs_one")
+    utils.check_properties(good)
+    for k, v in (("model_output", 5), ("env", ["a"]), ("reward_clipping", "x"), ("num_actors", 3)):
+        bad = dict(good)
+        bad[k] = v
+        with pytest.raises(AssertionError):
+            utils.check_properties(bad)
+
+
+# ---- trajectory ring ------------------------------------------------------------------------------
+def _traj(i, T=5, A=4, L=8, shape=(6, 6, 2)):
+    rng = np.random.default_rng(i)
+    return dict(s=np.full((T, *shape), i % 256, np.uint8), ns=None, r=np.full(T, float(i), np.float32),
+                d=rng.random(T) < 0.5, mu=rng.random((T, A)).astype(np.float32),
+                a=np.full(T, i, np.int32), pa=np.full(T, i + 1, np.int32),
+                h=rng.standard_normal((T, L)).astype(np.float32), c=rng.standard_normal((T, L)).astype(np.float32))
+
+
+def _push(q, t, **kw):
+    q.append_to_queue(0, t["s"], t["ns"], t["r"], t["d"], t["mu"], t["a"], t["pa"], t["h"], t["c"], **kw)
+
+
+def _queue(native, cap=8, batch=4):
+    from distributed_reinforcement_learning_b200.distributed_queue import buffer_queue
+    return buffer_queue.FIFOQueue(5, [6, 6, 2], 4, cap, batch, 2, 8, pinned=False)
+
+
+def test_ring_fifo_order_and_fields(native):
+    q = _queue(native)
+    q.set_session(object())
+    trajs = [_traj(i) for i in range(8)]
+    for t in trajs:
+        _push(q, t)
+    assert q.get_size() == 8
+    for base in (0, 4):
+        b = q.sample_batch()
+        assert b._fields == ('state', 'next_state', 'reward', 'done', 'behavior_policy', 'action',
+                             'previous_action', 'previous_h', 'previous_c')
+        assert b.next_state is None and b.state.shape == (4, 5, 6, 6, 2) and b.done.dtype == np.bool_
+        for j in range(4):
+            t = trajs[base + j]
+            assert np.array_equal(b.state[j], t["s"]) and np.array_equal(b.reward[j], t["r"])
+            assert np.array_equal(b.done[j], t["d"]) and np.array_equal(b.behavior_policy[j], t["mu"])
+            assert np.array_equal(b.action[j], t["a"]) and np.array_equal(b.previous_action[j], t["pa"])
+            assert np.array_equal(b.previous_h[j], t["h"]) and np.array_equal(b.previous_c[j], t["c"])
+        # the reference launcher np.stack()s each field (train_impala.py:100-108): must keep working
+        assert np.stack(b.state).shape == (4, 5, 6, 6, 2)
+    assert q.get_size() == 0
+    q.close()
+
+
+def test_ring_blocks_when_full_and_when_empty(native):
+    q = _queue(native, cap=4, batch=4)          # 2 batch slots
+    with pytest.raises(native.TimeoutError_):
+        q.sample_batch(timeout_ms=20)            # empty: fewer than batch trajectories
+    for i in range(8):
+        _push(q, _traj(i))
+    with pytest.raises(native.TimeoutError_):
+        _push(q, _traj(99), timeout_ms=20)       # both slots full
+    b = q.sample_batch()
+    assert int(b.action[0, 0]) == 0
+    with pytest.raises(native.TimeoutError_):
+        _push(q, _traj(99), timeout_ms=20)       # slot 0 is held by the consumer, slot 1 is full
+    b = q.sample_batch()                         # releases slot 0
+    assert int(b.action[0, 0]) == 4
+    _push(q, _traj(8), timeout_ms=200)
+    assert q.get_size() == 1
+    q.close()
+
+
+def test_ring_concurrent_producers_wrap_around(native):
+    q = _queue(native, cap=8, batch=4)
+    n_prod, per = 4, 12
+
+    def prod(k):
+        for i in range(per):
+            _push(q, _traj(k * 100 + i))
+    th = [threading.Thread(target=prod, args=(k,)) for k in range(n_prod)]
+    for t in th:
+        t.start()
+    seen = []
+    for _ in range(n_prod * per // 4):
+        b = q.sample_batch(timeout_ms=5000)
+        for j in range(4):
+            i = int(b.action[j, 0])
+            assert int(b.previous_action[j, 0]) == i + 1 and int(b.state[j, 0, 0, 0, 0]) == i % 256
+            seen.append(i)
+    for t in th:
+        t.join()
+    assert sorted(seen) == sorted(k * 100 + i for k in range(n_prod) for i in range(per))
+    for k in range(n_prod):                      # per-producer order is preserved (FIFO)
+        mine = [i for i in seen if i // 100 == k]
+        assert mine == sorted(mine)
+    q.close()
+
+
+def test_ring_rejects_bad_shapes(native):
+    q = _queue(native)
+    t = _traj(0)
+    t["r"] = np.zeros(4, np.float32)
+    with pytest.raises(ValueError):
+        _push(q, t)
+    from distributed_reinforcement_learning_b200.distributed_queue import buffer_queue
+    with pytest.raises(native.DrlError):
+        buffer_queue.FIFOQueue(5, [6, 6, 2], 4, 8, 0, 2, 8, pinned=False)
+    q.close()
+
+
+def test_agent_constructor_surface(native):
+    """Same 14 kwargs as impala.Agent (agent/impala.py:11-14, train_impala.py:48-62); no device work yet."""
+    import inspect
+    from distributed_reinforcement_learning_b200.agent import impala
+    names = list(inspect.signature(impala.Agent.__init__).parameters)[1:]
+    assert names == ["trajectory", "input_shape", "num_action", "lstm_hidden_size", "discount_factor",
+                     "start_learning_rate", "end_learning_rate", "learning_frame", "baseline_loss_coef",
+                     "entropy_coef", "gradient_clip_norm", "reward_clipping", "model_name", "learner_name"]
+    a = impala.Agent(20, [84, 84, 4], 18, 256, 0.99, 6e-4, 0.0, 1e9, 1.0, 0.05, 40.0, "abs_one", "learner", "learner")
+    for m in ("set_session", "train", "get_policy_and_action", "parameter_sync", "save_weights", "load_weights"):
+        assert callable(getattr(a, m))
+    with pytest.raises(AssertionError):
+        impala.Agent(20, [84, 84, 4], 18, 256, 0.99, 6e-4, 0.0, 1e9, 1.0, 0.05, 40.0, "bogus", "x", "learner")
+    a.set_session(None)
+    assert a._params.size == 4153267 and float(a._ms.min()) == 1.0
+
+
+def test_agent_checkpoint_roundtrip(native, tmp_path):
+    from distributed_reinforcement_learning_b200.agent import impala
+    kw = dict(trajectory=20, input_shape=[84, 84, 4], num_action=18, lstm_hidden_size=256, discount_factor=0.99,
+              start_learning_rate=6e-4, end_learning_rate=0.0, learning_frame=1e9, baseline_loss_coef=1.0,
+              entropy_coef=0.05, gradient_clip_norm=40.0, reward_clipping="abs_one", learner_name="learner")
+    a = impala.Agent(model_name="learner", **kw)
+    a.set_session(None)
+    a._step = 7
+    a.save_weights(str(tmp_path / "ckpt"))
+    b = impala.Agent(model_name="actor_0", **kw)
+    b.set_session(None)
+    assert not np.array_equal(a._params, b._params)
+    b.load_weights(str(tmp_path / "ckpt"))
+    assert np.array_equal(a._params, b._params) and b._step == 7
+    c = impala.Agent(model_name="actor_1", **kw)
+    c.set_session(None)
+    c.parameter_sync()                               # learner -> actor copy (utils.py:6-22)
+    assert np.array_equal(c._params, a._params)
+
+
+def test_shard_range(native):
+    from distributed_reinforcement_learning_b200.learner import shard_range
+    assert [shard_range(r, 8, 256) for r in (0, 7)] == [(0, 32), (224, 256)]
+    with pytest.raises(ValueError):
+        shard_range(0, 3, 32)
