@@ -139,11 +139,26 @@ def step_flops(B):
 
 
 # ---- CPU restatement of the reference (oracle) ---------------------------------------------------
+def usable_cores():
+    """Host cores this process may really use: min(affinity, cgroup CPU quota).  The gpurun boxes show 128
+    logical CPUs but carry a 16-CPU cgroup quota; 128 torch threads under that quota run 500x slower
+    (profiles/r01_cpu_threads_probe.txt), so the quota is what "all the host threads it can use" means."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def cpu_reference(steps, warmup, B=B_PER_GPU):
     import torch
     from oracle import impala_torch as it
     from oracle import synthetic
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     batch = synthetic.make_batch(B, T=T, A=A)
     args = [batch[k] for k in synthetic.TRAIN_FIELDS]

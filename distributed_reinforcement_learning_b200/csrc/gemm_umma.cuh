@@ -1,0 +1,408 @@
+// gemm_umma.cuh -- gather-GEMM on the 5th-generation tensor cores (tcgen05.mma, kind::tf32) with
+// fp32-grade accuracy by operand splitting ("3xTF32"):
+//
+//     x = hi + lo,  hi = rna_tf32(x),  lo = x - hi      (lo is exact in fp32, |lo| <= 2^-11 |x|)
+//     A*B ~= A_lo*B_hi + A_hi*B_lo + A_hi*B_hi           (dropped term A_lo*B_lo ~ 2^-22 relative)
+//
+// all three products accumulate in fp32 in ONE TMEM accumulator.  Same loader / epilogue functor
+// concepts as gemm_simt.cuh, so every layer of layers.cu can run on either core.
+//
+// Structure (one 128 x BN output tile per CTA, 160 threads, 1 CTA per SM):
+//   warps 0-3 : PRODUCERS, then EPILOGUE.  Each thread gathers float4 groups of A and B through the
+//               loader functors (im2col, concat, transposes happen here -- which is why TMA cannot
+//               stage these operands), splits them into hi/lo and writes both into the stage's
+//               shared-memory operand tiles in the canonical 128-byte-swizzled UMMA layout
+//               (K-major for kContigK loaders, MN-major otherwise), then fence.proxy.async and
+//               mbarrier-arrive on full[stage].
+//   warp 4    : TMEM allocation + MMA ISSUER: waits full[stage], one lane issues 3 x (BK/8)
+//               tcgen05.mma (M=128, N=BN, K=8) from shared-memory descriptors, then tcgen05.commit ->
+//               empty[stage]; after the last K tile tcgen05.commit -> acc_full.
+//   epilogue  : warps 0-3 read their 32 TMEM lanes (tcgen05.ld 32x32b.x32) and hand rows to the
+//               epilogue functor (bias/ReLU/mask/split-K partial ...).
+//
+// Canonical SWIZZLE_128B layouts (CuTe mma_traits_sm100.hpp::make_umma_desc), BK = 32 floats:
+//   K-major : row r is 128 contiguous bytes (32 floats of K) at r*128; the 16-byte chunk c of row r is
+//             stored at chunk position c ^ (r & 7)  (Swizzle<3,4,3>: address bits [4,7) ^= bits [7,10)).
+//             8-row groups are 1024 bytes apart (SBO = 1024).  A K=8 MMA slice j starts at +32*j bytes.
+//   MN-major: atoms of 32 (mn) x 8 (k): k-row kr is 128 contiguous bytes (32 mn values) at kr*128, chunk
+//             c = (mn%32)/4 stored at c ^ kr.  Atom (g = mn/32, kg = k/8) at (kg*(ROWS/32) + g)*1024:
+//             LBO (mn-group stride) = 1024, SBO (k-group stride) = (ROWS/32)*1024.  MMA slice j = atom row kg=j.
+// All operand tiles are 1024-byte aligned (base_offset = 0).
+#pragma once
+#include "common.cuh"
+
+namespace drl {
+namespace umma {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by one thread
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 32 lanes x 32 consecutive columns (one 32-bit word each) -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor: SWIZZLE_128B (layout_type 2), descriptor version 1 (sm_100), base_offset 0
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // version
+  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, dense, no negate; M=128
+__host__ __device__ constexpr uint32_t make_idesc(int N, bool a_mn_major, bool b_mn_major) {
+  return (1u << 4)                        // c_format  = F32
+         | (2u << 7)                      // a_format  = TF32
+         | (2u << 10)                     // b_format  = TF32
+         | ((a_mn_major ? 1u : 0u) << 15) // a_major
+         | ((b_mn_major ? 1u : 0u) << 16) // b_major
+         | ((uint32_t)(N >> 3) << 17)     // n_dim
+         | ((uint32_t)(128 >> 4) << 24);  // m_dim
+}
+
+__device__ __forceinline__ float tf32_hi(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ void split4(const float4& x, float4& h, float4& l) {
+  h.x = tf32_hi(x.x); h.y = tf32_hi(x.y); h.z = tf32_hi(x.z); h.w = tf32_hi(x.w);
+  l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
+}
+
+}  // namespace umma
+
+// One operand tile of a stage: ROWS (128 for A, BN for B) x 32 floats, SWIZZLE_128B.
+template <int ROWS, bool KMAJOR>
+struct UmmaTile {
+  static constexpr int BK = 32;
+  static constexpr int BYTES = ROWS * BK * 4;
+  static constexpr int LBO = KMAJOR ? 16 : 1024;                      // K-major: unused by hw (canonical value 1 unit)
+  static constexpr int SBO = KMAJOR ? 1024 : (ROWS / 32) * 1024;
+  // byte offset of the 16-byte chunk a loader group writes.
+  //   K-major : idx = row, k multiple of 4      MN-major : idx = row (multiple of 4), single k
+  __device__ static __forceinline__ int chunk_off(int idx, int k) {
+    if (KMAJOR) return idx * 128 + ((((k >> 2) ^ idx) & 7) << 4);
+    const int kr = k & 7, c = (idx & 31) >> 2;
+    return ((k >> 3) * (ROWS / 32) + (idx >> 5)) * 1024 + kr * 128 + ((c ^ kr) << 4);
+  }
+  // descriptor start offset of the j-th K=8 slice
+  __device__ static __forceinline__ int kslice_off(int j) { return KMAJOR ? j * 32 : j * SBO; }
+};
+
+template <int BN_, int STAGES_>
+struct UmmaCfg {
+  static constexpr int BM = 128, BN = BN_, BK = 32, STAGES = STAGES_;
+  static constexpr int NPROD = 128;     // producer / epilogue threads (warps 0-3)
+  static constexpr int NT = 160;        // + MMA warp
+  static constexpr int TMEM_COLS = BN;
+  static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 256, "BN must be a power of two in [32,256]");
+};
+
+template <class Cfg, class AL, class BL>
+struct UmmaSmem {
+  using TA = UmmaTile<Cfg::BM, AL::kContigK>;
+  using TB = UmmaTile<Cfg::BN, BL::kContigK>;
+  static constexpr int A_BYTES = TA::BYTES, B_BYTES = TB::BYTES;       // multiples of 1024
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;        // hi and lo copies of both operands
+  static constexpr int AUX_BYTES = 1024 + (BL::kContigK ? 0 : Cfg::NPROD * 16);   // barriers, tmem ptr, colsum scratch
+  static constexpr int BYTES = Cfg::STAGES * STAGE_BYTES + AUX_BYTES + 1024;      // + alignment slack
+};
+
+template <class Cfg, class AL, class BL, class EP>
+__global__ void __launch_bounds__(Cfg::NT, 1)
+gemm_umma_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, int kchunk, int kstep) {
+  constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES, NPROD = Cfg::NPROD;
+  constexpr bool AK = AL::kContigK, BKc = BL::kContigK;
+  using SM = UmmaSmem<Cfg, AL, BL>;
+  using TA = typename SM::TA;
+  using TB = typename SM::TB;
+  constexpr int NGA = BM * BK / 4, NGB = BN * BK / 4;       // float4 groups per stage
+  constexpr int GA = NGA / NPROD, GB = NGB / NPROD;          // per producer thread (8 and BN/16)
+  static_assert(NGA % NPROD == 0 && NGB % NPROD == 0, "groups must divide among producers");
+  constexpr bool kColSum = EP::kColSum && !BKc;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* aux = smem + STAGES * SM::STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(aux);
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
+  float4* cs_scratch = reinterpret_cast<float4*>(aux + 1024);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int z = blockIdx.z;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int k0 = z * kstep;
+  const int k1 = min(K, k0 + kchunk);
+  const int ntiles = (k1 - k0 + BK - 1) / BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      umma::mbar_init(&full[s], NPROD);
+      umma::mbar_init(&empty[s], 1);
+    }
+    umma::mbar_init(acc_full, 1);
+    umma::fence_barrier_init();
+  }
+  if (warp == 4) umma::tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp < 4) {
+    // ================= PRODUCERS =================
+    // K-major operand : group g -> row g/8, chunk g%8  (8 lanes cover one 128-byte row: coalesced global
+    //                   read of 128 contiguous bytes, conflict-free swizzled 16-byte stores)
+    // MN-major operand: group g -> k = g/(ROWS/4), quad q = g%(ROWS/4)  (8 lanes cover 32 contiguous mn
+    //                   values of one k: coalesced, conflict-free)
+    typename AL::Row arow[GA];
+    typename BL::Row brow[GB];
+    int a_k[GA], a_o[GA], b_k[GB], b_o[GB];
+#pragma unroll
+    for (int i = 0; i < GA; ++i) {
+      const int g = tid + i * NPROD;
+      if (AK) {
+        const int r = g >> 3, kq = g & 7;
+        arow[i] = al.row(z, (m0 + r < M) ? m0 + r : -1);
+        a_k[i] = kq * 4;
+        a_o[i] = TA::chunk_off(r, kq * 4);
+      } else {
+        const int q = g % (BM / 4), kk = g / (BM / 4);
+        arow[i] = al.row(z, (m0 + q * 4 < M) ? m0 + q * 4 : -1);
+        a_k[i] = kk;
+        a_o[i] = TA::chunk_off(q * 4, kk);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < GB; ++i) {
+      const int g = tid + i * NPROD;
+      if (BKc) {
+        const int r = g >> 3, kq = g & 7;
+        brow[i] = bl.row(z, (n0 + r < N) ? n0 + r : -1);
+        b_k[i] = kq * 4;
+        b_o[i] = TB::chunk_off(r, kq * 4);
+      } else {
+        const int q = g % (BN / 4), kk = g / (BN / 4);
+        brow[i] = bl.row(z, (n0 + q * 4 < N) ? n0 + q * 4 : -1);
+        b_k[i] = kk;
+        b_o[i] = TB::chunk_off(q * 4, kk);
+      }
+    }
+    float4 csum[GB];
+#pragma unroll
+    for (int i = 0; i < GB; ++i) csum[i] = zero4();
+
+    for (int t = 0; t < ntiles; ++t) {
+      const int s = t % STAGES;
+      const uint32_t ph = (t / STAGES) & 1;
+      const int kb = k0 + t * BK;
+      float4 ra[GA], rb[GB];          // global loads are issued before waiting for the slot
+#pragma unroll
+      for (int i = 0; i < GA; ++i) {
+        const int k = kb + a_k[i];
+        ra[i] = (k < k1) ? al.load(arow[i], k) : zero4();
+      }
+#pragma unroll
+      for (int i = 0; i < GB; ++i) {
+        const int k = kb + b_k[i];
+        rb[i] = (k < k1) ? bl.load(brow[i], k) : zero4();
+        if (kColSum) { csum[i].x += rb[i].x; csum[i].y += rb[i].y; csum[i].z += rb[i].z; csum[i].w += rb[i].w; }
+      }
+      umma::mbar_wait(&empty[s], ph ^ 1);
+      uint8_t* st = smem + s * SM::STAGE_BYTES;
+      uint8_t* a_hi = st;
+      uint8_t* a_lo = st + SM::A_BYTES;
+      uint8_t* b_hi = st + 2 * SM::A_BYTES;
+      uint8_t* b_lo = b_hi + SM::B_BYTES;
+#pragma unroll
+      for (int i = 0; i < GA; ++i) {
+        float4 h, l;
+        umma::split4(ra[i], h, l);
+        *reinterpret_cast<float4*>(a_hi + a_o[i]) = h;
+        *reinterpret_cast<float4*>(a_lo + a_o[i]) = l;
+      }
+#pragma unroll
+      for (int i = 0; i < GB; ++i) {
+        float4 h, l;
+        umma::split4(rb[i], h, l);
+        *reinterpret_cast<float4*>(b_hi + b_o[i]) = h;
+        *reinterpret_cast<float4*>(b_lo + b_o[i]) = l;
+      }
+      umma::fence_proxy_async();       // generic-proxy writes -> visible to the tensor-core (async) proxy
+      umma::mbar_arrive(&full[s]);
+    }
+
+    // bias-gradient row: column sums of B (dY) over this CTA's K range, reduced in fixed order
+    if (kColSum && blockIdx.x == 0) {
+      // thread's groups: q = (tid + i*NPROD) % (BN/4).  NPROD is a multiple of BN/4, so q = tid % (BN/4) for all i.
+      float4 acc = zero4();
+#pragma unroll
+      for (int i = 0; i < GB; ++i) { acc.x += csum[i].x; acc.y += csum[i].y; acc.z += csum[i].z; acc.w += csum[i].w; }
+      cs_scratch[tid] = acc;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (tid < BN / 4) {
+        float4 tot = zero4();
+        for (int j = tid; j < NPROD; j += BN / 4) {
+          const float4 v = cs_scratch[j];
+          tot.x += v.x; tot.y += v.y; tot.z += v.z; tot.w += v.w;
+        }
+        const int n = n0 + tid * 4;
+        if (n < N) ep.store_colsum(z, n, tot.x);
+        if (n + 1 < N) ep.store_colsum(z, n + 1, tot.y);
+        if (n + 2 < N) ep.store_colsum(z, n + 2, tot.z);
+        if (n + 3 < N) ep.store_colsum(z, n + 3, tot.w);
+      }
+    }
+
+    // ================= EPILOGUE =================
+    umma::mbar_wait(acc_full, 0);
+    umma::tc_fence_after();
+    const int m = m0 + warp * 32 + lane;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float v[32];
+      umma::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      if (m < M) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int n = n0 + c0 + j;
+          if (n + 3 < N) {
+            const float o[4] = {v[j], v[j + 1], v[j + 2], v[j + 3]};
+            ep.template store<4>(z, m, n, o);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (n + q < N) {
+                const float o[1] = {v[j + q]};
+                ep.template store<1>(z, m, n + q, o);
+              }
+          }
+        }
+      }
+    }
+    umma::tc_fence_before();
+  } else {
+    // ================= MMA ISSUER (warp 4) =================
+    constexpr uint32_t idesc = umma::make_idesc(BN, !AK, !BKc);
+    for (int t = 0; t < ntiles; ++t) {
+      const int s = t % STAGES;
+      const uint32_t ph = (t / STAGES) & 1;
+      umma::mbar_wait(&full[s], ph);
+      umma::tc_fence_after();
+      if (lane == 0) {
+        const uint32_t st = umma::smem_u32(smem + s * SM::STAGE_BYTES);
+        const uint32_t a_hi = st, a_lo = st + SM::A_BYTES, b_hi = st + 2 * SM::A_BYTES, b_lo = b_hi + SM::B_BYTES;
+#pragma unroll
+        for (int j = 0; j < BK / 8; ++j) {
+          const uint32_t ao = TA::kslice_off(j), bo = TB::kslice_off(j);
+          const uint64_t dah = umma::make_desc(a_hi + ao, TA::LBO, TA::SBO);
+          const uint64_t dal = umma::make_desc(a_lo + ao, TA::LBO, TA::SBO);
+          const uint64_t dbh = umma::make_desc(b_hi + bo, TB::LBO, TB::SBO);
+          const uint64_t dbl = umma::make_desc(b_lo + bo, TB::LBO, TB::SBO);
+          umma::mma_tf32(tmem_base, dal, dbh, idesc, (t > 0 || j > 0) ? 1u : 0u);   // small terms first
+          umma::mma_tf32(tmem_base, dah, dbl, idesc, 1u);
+          umma::mma_tf32(tmem_base, dah, dbh, idesc, 1u);
+        }
+        umma::mma_commit(&empty[s]);            // frees the smem slot once these MMAs have read it
+        if (t == ntiles - 1) umma::mma_commit(acc_full);
+      }
+      __syncwarp();
+    }
+    umma::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    umma::tc_fence_after();
+    umma::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <class Cfg, class AL, class BL, class EP>
+inline int launch_gemm_umma(cudaStream_t s, const AL& al, const BL& bl, const EP& ep, int M, int N, int K,
+                            int zcount, int kchunk, int kstep) {
+  using SM = UmmaSmem<Cfg, AL, BL>;
+  static bool attr_done = false;
+  auto kern = gemm_umma_kernel<Cfg, AL, BL, EP>;
+  if (!attr_done) {
+    DRL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::BYTES));
+    attr_done = true;
+  }
+  if ((AL::kContigK || BL::kContigK) && (K % 4 != 0 || kchunk % 4 != 0)) {
+    set_error("gemm_umma: K (%d) and kchunk (%d) must be multiples of 4 for K-contiguous operands", K, kchunk);
+    return DRL_ERR_INVALID;
+  }
+  if (kchunk < 1 || K < 1) { set_error("gemm_umma: empty K range"); return DRL_ERR_INVALID; }
+  dim3 grid(cdiv(M, Cfg::BM), cdiv(N, Cfg::BN), zcount);
+  kern<<<grid, Cfg::NT, SM::BYTES, s>>>(al, bl, ep, M, N, K, kchunk, kstep);
+  DRL_CHECK_LAUNCH();
+  return DRL_OK;
+}
+
+}  // namespace drl

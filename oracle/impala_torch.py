@@ -104,19 +104,59 @@ def _conv2d_tf(x_nhwc, w_hwio, b, stride):
     return y.permute(0, 2, 3, 1)
 
 
+# ReLU activation-pattern override (test aid).  ReLU' is discontinuous at 0: when a pre-activation is
+# within float32 rounding of zero, a float32 implementation and this float64 oracle can legitimately
+# disagree on the mask, and that single flip changes the gradient of the whole image by O(1e-3).
+# ``activation_pattern(masks)`` makes the oracle evaluate relu(x) as x * mask with masks observed on the
+# implementation under test (forward AND backward then follow the same branch) and records every
+# element where sign(x) disagrees with the mask together with |x| there, so the caller can assert that
+# flips are rare and only happen at |x| ~ 0.
+_PATTERN = {"masks": None, "flips": 0, "elems": 0, "max_abs_at_flip": 0.0}
+
+
+class activation_pattern:
+    def __init__(self, masks):
+        self.masks = masks
+
+    def __enter__(self):
+        _PATTERN.update(masks=self.masks, flips=0, elems=0, max_abs_at_flip=0.0)
+        return _PATTERN
+
+    def __exit__(self, *exc):
+        _PATTERN["masks"] = None
+        return False
+
+
+def _relu(x, name, index=None):
+    masks = _PATTERN["masks"]
+    if masks is None or name not in masks:
+        return F.relu(x)
+    m = masks[name]
+    if index is not None:
+        m = m[index]
+    m = m.reshape(x.shape).to(torch.bool)
+    flip = (x > 0) != m
+    n = int(flip.sum())
+    _PATTERN["elems"] += x.numel()
+    if n:
+        _PATTERN["flips"] += n
+        _PATTERN["max_abs_at_flip"] = max(_PATTERN["max_abs_at_flip"], float(x.detach().abs()[flip].max()))
+    return x * m.to(x.dtype)
+
+
 def attention_cnn(p, x):
     """model/impala_actor_critic.py:5-10; returns (flatten HWC, intermediates)."""
-    a1 = F.relu(_conv2d_tf(x, p["conv1.w"], p["conv1.b"], 4))
-    a2 = F.relu(_conv2d_tf(a1, p["conv2.w"], p["conv2.b"], 2))
-    a3 = F.relu(_conv2d_tf(a2, p["conv3.w"], p["conv3.b"], 1))
+    a1 = _relu(_conv2d_tf(x, p["conv1.w"], p["conv1.b"], 4), "a1")
+    a2 = _relu(_conv2d_tf(a1, p["conv2.w"], p["conv2.b"], 2), "a2")
+    a3 = _relu(_conv2d_tf(a2, p["conv3.w"], p["conv3.b"], 1), "a3")
     return a3.reshape(a3.shape[0], -1), (a1, a2, a3)
 
 
 def action_embedding(p, previous_action, num_action):
     """model/impala_actor_critic.py:12-16."""
     onehot = F.one_hot(previous_action.long(), num_action).to(p["emb1.w"].dtype)
-    x = F.relu(onehot @ p["emb1.w"] + p["emb1.b"])
-    return F.relu(x @ p["emb2.w"] + p["emb2.b"])
+    x = _relu(onehot @ p["emb1.w"] + p["emb1.b"], "e1", previous_action.long())
+    return _relu(x @ p["emb2.w"] + p["emb2.b"], "emb", previous_action.long())
 
 
 def lstm(p, inputs, initial_h, initial_c):
@@ -132,8 +172,8 @@ def lstm(p, inputs, initial_h, initial_c):
 
 def fully_connected(p, x, prefix):
     """model/impala_actor_critic.py:27-30 with hidden_list=[256,256]."""
-    x = F.relu(x @ p[prefix + "1.w"] + p[prefix + "1.b"])
-    x = F.relu(x @ p[prefix + "2.w"] + p[prefix + "2.b"])
+    x = _relu(x @ p[prefix + "1.w"] + p[prefix + "1.b"], prefix + "1")
+    x = _relu(x @ p[prefix + "2.w"] + p[prefix + "2.b"], prefix + "2")
     return x @ p[prefix + "3.w"] + p[prefix + "3.b"]
 
 
@@ -335,9 +375,14 @@ class Learner:
     def gradients(self, *batch, **kbatch):
         out = self.losses(*batch, **kbatch)
         names = list(self.params)
-        grads = torch.autograd.grad(out["total_loss"], [self.params[n] for n in names], allow_unused=True)
+        extra = []
+        if out.get("taps") is not None:          # also dL/d(activation) for the layer-wise parity diagnostics
+            extra = [k for k in ("a1", "a2", "a3", "h1") if k in out["taps"]]
+        grads = torch.autograd.grad(out["total_loss"], [self.params[n] for n in names] +
+                                    [out["taps"][k] for k in extra], allow_unused=True)
         g = OrderedDict((n, (gi if gi is not None else torch.zeros_like(self.params[n])))
                         for n, gi in zip(names, grads))
+        out["act_grads"] = {k: gi for k, gi in zip(extra, grads[len(names):])}
         return out, g
 
     # ---- Agent.train (agent/impala.py:95-100,132-148) ----------------------------
