@@ -24,9 +24,7 @@
 //   K-major : row r is 128 contiguous bytes (32 floats of K) at r*128; the 16-byte chunk c of row r is
 //             stored at chunk position c ^ (r & 7)  (Swizzle<3,4,3>: address bits [4,7) ^= bits [7,10)).
 //             8-row groups are 1024 bytes apart (SBO = 1024).  A K=8 MMA slice j starts at +32*j bytes.
-//   MN-major: atoms of 32 (mn) x 8 (k): k-row kr is 128 contiguous bytes (32 mn values) at kr*128, chunk
-//             c = (mn%32)/4 stored at c ^ kr.  Atom (g = mn/32, kg = k/8) at (kg*(ROWS/32) + g)*1024:
-//             LBO (mn-group stride) = 1024, SBO (k-group stride) = (ROWS/32)*1024.  MMA slice j = atom row kg=j.
+//   MN-major: SWIZZLE_128B_BASE32B, atoms of 32 (mn) x 4 (k) -- see UmmaTile below.
 // All operand tiles are 1024-byte aligned (base_offset = 0).
 #pragma once
 #include "common.cuh"
@@ -103,14 +101,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// shared-memory matrix descriptor: SWIZZLE_128B (layout_type 2), descriptor version 1 (sm_100), base_offset 0
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): descriptor version 1 (sm_100), base_offset 0,
+// layout_type 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;   // version
-  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  d |= (uint64_t)layout_type << 61;
   return d;
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, dense, no negate; M=128
@@ -136,22 +136,30 @@ __device__ __forceinline__ void split4(const float4& x, float4& h, float4& l) {
 
 }  // namespace umma
 
-// One operand tile of a stage: ROWS (128 for A, BN for B) x 32 floats, SWIZZLE_128B.
+// One operand tile of a stage: ROWS (128 for A, BN for B) x 32 floats.
+//   K-major : SWIZZLE_128B (layout type 2), rows of 128 bytes, 16-byte chunks XOR (row & 7).
+//   MN-major: SWIZZLE_128B_BASE32B (layout type 1) -- the ONLY shared-memory layout the hardware accepts for
+//             MN-major tf32 operands (cutlass sm100_common.inl:92).  Atoms of 32 (mn) x 4 (k) = 512 bytes:
+//             k-row kr is 128 contiguous bytes (32 mn values), its four 32-byte chunks XOR kr
+//             (Swizzle<2,5,2>: byte-address bits [5,7) ^= bits [7,9)).  Atom (g = mn/32, kg = k/4) sits at
+//             (kg*(ROWS/32) + g)*512: LBO (mn-group stride) = 512, SBO (k-group stride) = (ROWS/32)*512.
+//             A K=8 MMA slice j covers k-groups 2j, 2j+1 and starts at j*2*SBO.
 template <int ROWS, bool KMAJOR>
 struct UmmaTile {
   static constexpr int BK = 32;
   static constexpr int BYTES = ROWS * BK * 4;
-  static constexpr int LBO = KMAJOR ? 16 : 1024;                      // K-major: unused by hw (canonical value 1 unit)
-  static constexpr int SBO = KMAJOR ? 1024 : (ROWS / 32) * 1024;
+  static constexpr int LBO = KMAJOR ? 16 : 512;                       // K-major: unused by hw (canonical value 1 unit)
+  static constexpr int SBO = KMAJOR ? 1024 : (ROWS / 32) * 512;
+  static constexpr int LAYOUT_TYPE = KMAJOR ? 2 : 1;
   // byte offset of the 16-byte chunk a loader group writes.
   //   K-major : idx = row, k multiple of 4      MN-major : idx = row (multiple of 4), single k
   __device__ static __forceinline__ int chunk_off(int idx, int k) {
     if (KMAJOR) return idx * 128 + ((((k >> 2) ^ idx) & 7) << 4);
-    const int kr = k & 7, c = (idx & 31) >> 2;
-    return ((k >> 3) * (ROWS / 32) + (idx >> 5)) * 1024 + kr * 128 + ((c ^ kr) << 4);
+    const int kr = k & 3, c32 = (idx & 31) >> 3, half = (idx & 7) >> 2;
+    return ((k >> 2) * (ROWS / 32) + (idx >> 5)) * 512 + kr * 128 + ((c32 ^ kr) << 5) + (half << 4);
   }
   // descriptor start offset of the j-th K=8 slice
-  __device__ static __forceinline__ int kslice_off(int j) { return KMAJOR ? j * 32 : j * SBO; }
+  __device__ static __forceinline__ int kslice_off(int j) { return KMAJOR ? j * 32 : j * 2 * SBO; }
 };
 
 template <int BN_, int STAGES_>
@@ -362,10 +370,10 @@ gemm_umma_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, int
 #pragma unroll
         for (int j = 0; j < BK / 8; ++j) {
           const uint32_t ao = TA::kslice_off(j), bo = TB::kslice_off(j);
-          const uint64_t dah = umma::make_desc(a_hi + ao, TA::LBO, TA::SBO);
-          const uint64_t dal = umma::make_desc(a_lo + ao, TA::LBO, TA::SBO);
-          const uint64_t dbh = umma::make_desc(b_hi + bo, TB::LBO, TB::SBO);
-          const uint64_t dbl = umma::make_desc(b_lo + bo, TB::LBO, TB::SBO);
+          const uint64_t dah = umma::make_desc(a_hi + ao, TA::LBO, TA::SBO, TA::LAYOUT_TYPE);
+          const uint64_t dal = umma::make_desc(a_lo + ao, TA::LBO, TA::SBO, TA::LAYOUT_TYPE);
+          const uint64_t dbh = umma::make_desc(b_hi + bo, TB::LBO, TB::SBO, TB::LAYOUT_TYPE);
+          const uint64_t dbl = umma::make_desc(b_lo + bo, TB::LBO, TB::SBO, TB::LAYOUT_TYPE);
           umma::mma_tf32(tmem_base, dal, dbh, idesc, (t > 0 || j > 0) ? 1u : 0u);   // small terms first
           umma::mma_tf32(tmem_base, dah, dbl, idesc, 1u);
           umma::mma_tf32(tmem_base, dah, dbh, idesc, 1u);

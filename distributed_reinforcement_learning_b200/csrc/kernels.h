@@ -79,15 +79,21 @@ struct VtraceOut {       // parity taps, batch-major [B, T-2]
 
 constexpr int kLstmSplits = 4;
 
+// math_mode 0 in drl_learner_config resolves to this (1 = FP32 FFMA, 2 = tcgen05 3xTF32)
+#ifndef DRL_DEFAULT_MATH_MODE
+#define DRL_DEFAULT_MATH_MODE 1
+#endif
+
 // Per-kernel device timing (learner.cu): when a profile run is active, prof_mark records a CUDA event
 // on the launching stream before each named launch; otherwise it is a no-op.
 void prof_mark(cudaStream_t s, const char* name);
 
 // ---- layers.cu ----------------------------------------------------------------------------
+// mode: 1 = FP32-FFMA gather-GEMM, 2 = tcgen05 3xTF32 gather-GEMM for the large contractions
 int net_forward(cudaStream_t s, const ParamLayout& pl, const float* params, const Inputs& in, const Acts& act,
-                int B, int T);
+                int B, int T, int mode);
 int net_backward(cudaStream_t s, const ParamLayout& pl, const float* params, float* grads, const Inputs& in,
-                 const Acts& act, const Bwd& bwd, int B, int T);
+                 const Acts& act, const Bwd& bwd, int B, int T, int mode);
 size_t wgrad_partial_floats(int B, int T);
 int forward_launch_count();
 int backward_launch_count();

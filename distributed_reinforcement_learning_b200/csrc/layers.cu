@@ -1,10 +1,13 @@
 // layers.cu -- forward and backward of the IMPALA actor-critic (model/impala_actor_critic.py:33-42)
 // over M = B*T independent rows (the LSTM is a single step from fed state, :18-25 / :73-82, so
 // time is embarrassingly parallel; only T distinct forwards exist).
-// Every dense contraction is one launch of the gather-GEMM in gemm_simt.cuh.
+// Every dense contraction is one launch of a gather-GEMM: the FP32-FFMA core (gemm_simt.cuh, math
+// mode 1) or the tcgen05 3xTF32 tensor-core core (gemm_umma.cuh, math mode 2) -- same loaders and
+// epilogues.  The small head layers (M x 256 x 256) always use the FFMA core.
 #include <algorithm>
 
 #include "gemm_simt.cuh"
+#include "gemm_umma.cuh"
 #include "kernels.h"
 #include "loaders.cuh"
 
@@ -52,28 +55,42 @@ using Conv2DA = ConvDgradA<9, 9, 64, 2, 4, 4, 10, 10>;
 using Conv2DB = ConvDgradB<32, 64, 2, 4, 4>;
 using Conv2DE = EpConvDx<20, 20, 32, 2, 10, 10>;
 
+using U32 = UmmaCfg<32, 4>;     // 40 KB / stage
+using U64 = UmmaCfg<64, 4>;     // 48 KB / stage
+using U128 = UmmaCfg<128, 3>;   // 64 KB / stage
+
 static int g_fwd_launches = 0, g_bwd_launches = 0;
 int forward_launch_count() { return g_fwd_launches; }
 int backward_launch_count() { return g_bwd_launches; }
 
-// name the launch for the per-kernel profile, run it, count it
-#define GEMM(name, Cfg, ...)                               \
-  do {                                                     \
-    prof_mark(s, name);                                    \
-    DRL_TRY((launch_gemm_simt<Cfg>(s, __VA_ARGS__)));      \
-    ++n;                                                   \
+// name the launch for the per-kernel profile, run it on the selected core, count it
+#define GEMM(name, SCfg, UCfg, ...)                          \
+  do {                                                       \
+    prof_mark(s, name);                                      \
+    if (mode == 2) {                                         \
+      DRL_TRY((launch_gemm_umma<UCfg>(s, __VA_ARGS__)));     \
+    } else {                                                 \
+      DRL_TRY((launch_gemm_simt<SCfg>(s, __VA_ARGS__)));     \
+    }                                                        \
+    ++n;                                                     \
   } while (0)
-#define KERNEL(name, call, cnt)                            \
-  do {                                                     \
-    prof_mark(s, name);                                    \
-    DRL_TRY(call);                                         \
-    n += (cnt);                                            \
+#define GEMM_FFMA(name, SCfg, ...)                           \
+  do {                                                       \
+    prof_mark(s, name);                                      \
+    DRL_TRY((launch_gemm_simt<SCfg>(s, __VA_ARGS__)));       \
+    ++n;                                                     \
+  } while (0)
+#define KERNEL(name, call, cnt)                              \
+  do {                                                       \
+    prof_mark(s, name);                                      \
+    DRL_TRY(call);                                           \
+    n += (cnt);                                              \
   } while (0)
 
-// split-K plan: about two waves of CTAs on 148 SMs
+// split-K plan: about `waves` waves of CTAs on 148 SMs
 struct SplitPlan { int splits, kchunk; };
-static SplitPlan plan_split(int K, int tiles_mn, int bk) {
-  int target = (2 * 148 + tiles_mn - 1) / tiles_mn;
+static SplitPlan plan_split(int K, int tiles_mn, int bk, int waves) {
+  int target = (waves * 148 + tiles_mn - 1) / tiles_mn;
   if (target < 1) target = 1;
   int kchunk = (K + target - 1) / target;
   kchunk = (kchunk + bk - 1) / bk * bk;
@@ -83,18 +100,30 @@ static SplitPlan plan_split(int K, int tiles_mn, int bk) {
   p.splits = (K + kchunk - 1) / kchunk;
   return p;
 }
+// the conv weight-gradient plans (mode 1: FFMA tiles, 2 waves; mode 2: 128-row UMMA tiles, 1 CTA/SM)
+static SplitPlan plan_conv1_wgrad(int Mb, int mode) {
+  return mode == 2 ? plan_split(Mb * 400, 2, 32, 1) : plan_split(Mb * 400, cdiv(256, CfgWg1::BM), 16, 2);
+}
+static SplitPlan plan_conv2_wgrad(int Mb, int mode) {
+  return mode == 2 ? plan_split(Mb * 81, 4, 32, 1) : plan_split(Mb * 81, cdiv(512, CfgBig::BM), 16, 2);
+}
+static SplitPlan plan_conv3_wgrad(int Mb, int mode) {
+  return mode == 2 ? plan_split(Mb * 49, 5, 32, 1) : plan_split(Mb * 49, cdiv(576, CfgBig::BM), 16, 2);
+}
 
 size_t wgrad_partial_floats(int B, int T) {
   const int Mb = B * (T - 2);
   size_t mx = 0;
-  mx = std::max(mx, (size_t)plan_split(Mb * 400, cdiv(256, CfgWg1::BM), 16).splits * 257 * 32);
-  mx = std::max(mx, (size_t)plan_split(Mb * 81, cdiv(512, CfgBig::BM), 16).splits * 513 * 64);
-  mx = std::max(mx, (size_t)plan_split(Mb * 49, cdiv(576, CfgBig::BM), 16).splits * 577 * 64);
+  for (int mode = 1; mode <= 2; ++mode) {
+    mx = std::max(mx, (size_t)plan_conv1_wgrad(Mb, mode).splits * 257 * 32);
+    mx = std::max(mx, (size_t)plan_conv2_wgrad(Mb, mode).splits * 513 * 64);
+    mx = std::max(mx, (size_t)plan_conv3_wgrad(Mb, mode).splits * 577 * 64);
+  }
   return mx;
 }
 
 int net_forward(cudaStream_t s, const ParamLayout& pl, const float* P, const Inputs& in, const Acts& act, int B,
-                int T) {
+                int T, int mode) {
   const int M = B * T;
   const RowMap map{B, T};
   int n = 0;
@@ -103,21 +132,21 @@ int net_forward(cudaStream_t s, const ParamLayout& pl, const float* P, const Inp
     Conv1A al{in.frames, map};
     PlainB bl{P + pl.conv1_w, 32, 0};
     EpConv1 ep{act.a1, 32, P + pl.conv1_b};
-    GEMM("conv1_fwd", CfgN32, al, bl, ep, M * 400, 32, 256, 1, 256, 0);
+    GEMM("conv1_fwd", CfgN32, U32, al, bl, ep, M * 400, 32, 256, 1, 256, 0);
   }
   // conv2 -> a2 [M,9,9,64]   (:7)
   {
     Conv2A al{act.a1, map};
     PlainB bl{P + pl.conv2_w, 64, 0};
     EpBiasAct<true, true> ep{act.a2, 64, 0, P + pl.conv2_b, 0, 1.0f};
-    GEMM("conv2_fwd", CfgBig, al, bl, ep, M * 81, 64, 512, 1, 512, 0);
+    GEMM("conv2_fwd", CfgBig, U64, al, bl, ep, M * 81, 64, 512, 1, 512, 0);
   }
   // conv3 -> a3 [M,7,7,64] = flatten HWC [M,3136]   (:8-10)
   {
     Conv3A al{act.a2, map};
     PlainB bl{P + pl.conv3_w, 64, 0};
     EpBiasAct<true, true> ep{act.a3, 64, 0, P + pl.conv3_b, 0, 1.0f};
-    GEMM("conv3_fwd", CfgBig, al, bl, ep, M * 49, 64, 576, 1, 576, 0);
+    GEMM("conv3_fwd", CfgBig, U64, al, bl, ep, M * 49, 64, 576, 1, 576, 0);
   }
   // action embedding table (:12-16): only A distinct inputs exist
   KERNEL("emb_fwd",
@@ -127,8 +156,8 @@ int net_forward(cudaStream_t s, const ParamLayout& pl, const float* P, const Inp
     LstmA al{act.a3, act.table, in.pa, in.h0, map};
     PlainB bl{P + pl.lstm_w, Geo::G4, 0};
     EpRaw<false> ep{act.zpart, Geo::G4, (size_t)M * Geo::G4, 1.0f, 0, Geo::G4};
-    const int kchunk = Geo::XK / kLstmSplits;   // 912 = 57 * 16
-    GEMM("lstm_fwd", CfgMid, al, bl, ep, M, Geo::G4, Geo::XK, kLstmSplits, kchunk, kchunk);
+    const int kchunk = (mode == 2) ? 928 : Geo::XK / kLstmSplits;   // 29 x 32 | 57 x 16 ; 4 splits either way
+    GEMM("lstm_fwd", CfgMid, U128, al, bl, ep, M, Geo::G4, Geo::XK, kLstmSplits, kchunk, kchunk);
   }
   KERNEL("lstm_gates_fwd",
          lstm_gates_forward(s, act.zpart, kLstmSplits, P + pl.lstm_b, in.c0, act.gates, act.c1, act.tc1, act.h1, M, B,
@@ -139,13 +168,13 @@ int net_forward(cudaStream_t s, const ParamLayout& pl, const float* P, const Inp
     PlainA al{act.h1, Geo::L, 0};
     PlainB bl{P + pl.actor1_w, Geo::HID, head_stride};
     EpBiasAct<true, true> ep{act.hid1, Geo::HID, (size_t)M * Geo::HID, P + pl.actor1_b, head_stride, 1.0f};
-    GEMM("heads_l1_fwd", CfgSmall, al, bl, ep, M, Geo::HID, Geo::L, 2, Geo::L, 0);
+    GEMM_FFMA("heads_l1_fwd", CfgSmall, al, bl, ep, M, Geo::HID, Geo::L, 2, Geo::L, 0);
   }
   {
     PlainA al{act.hid1, Geo::HID, (size_t)M * Geo::HID};
     PlainB bl{P + pl.actor2_w, Geo::HID, head_stride};
     EpBiasAct<true, true> ep{act.hid2, Geo::HID, (size_t)M * Geo::HID, P + pl.actor2_b, head_stride, 1.0f};
-    GEMM("heads_l2_fwd", CfgSmall, al, bl, ep, M, Geo::HID, Geo::HID, 2, Geo::HID, 0);
+    GEMM_FFMA("heads_l2_fwd", CfgSmall, al, bl, ep, M, Geo::HID, Geo::HID, 2, Geo::HID, 0);
   }
   KERNEL("heads_out_fwd",
          heads_out_forward(s, act.hid2, act.hid2 + (size_t)M * Geo::HID, P + pl.actor3_w, P + pl.actor3_b,
@@ -155,7 +184,7 @@ int net_forward(cudaStream_t s, const ParamLayout& pl, const float* P, const Inp
 }
 
 int net_backward(cudaStream_t s, const ParamLayout& pl, const float* P, float* G, const Inputs& in, const Acts& act,
-                 const Bwd& bw, int B, int T) {
+                 const Bwd& bw, int B, int T, int mode) {
   const int M = B * T;
   const int Mb = B * (T - 2);   // rows t <= T-3 are the contiguous prefix (time-major)
   const RowMap map{B, T};
@@ -171,37 +200,37 @@ int net_backward(cudaStream_t s, const ParamLayout& pl, const float* P, float* G
     PlainAT al{act.hid2, Geo::HID, 0};
     PlainB bl{bw.dlogits, 32, 0};
     EpRaw<true> ep{G + pl.actor3_w, A, 0, 1.0f, Geo::HID, A};
-    GEMM("actor3_wgrad", CfgSmall, al, bl, ep, Geo::HID, 32, Mb, 1, Mb, 0);
+    GEMM_FFMA("actor3_wgrad", CfgSmall, al, bl, ep, Geo::HID, 32, Mb, 1, Mb, 0);
   }
   {  // d critic3 [256(+1), 1]
     PlainAT al{act.hid2 + (size_t)M * Geo::HID, Geo::HID, 0};
     PlainB bl{bw.dv, 32, 0};
     EpRaw<true> ep{G + pl.critic3_w, 1, 0, 1.0f, Geo::HID, 1};
-    GEMM("critic3_wgrad", CfgSmall, al, bl, ep, Geo::HID, 32, Mb, 1, Mb, 0);
+    GEMM_FFMA("critic3_wgrad", CfgSmall, al, bl, ep, Geo::HID, 32, Mb, 1, Mb, 0);
   }
   {  // d {actor2, critic2} = hid1^T dhid2
     PlainAT al{act.hid1, Geo::HID, (size_t)M * Geo::HID};
     PlainB bl{bw.dhid2, Geo::HID, (size_t)Mb * Geo::HID};
     EpRaw<true> ep{G + pl.actor2_w, Geo::HID, head_stride, 1.0f, Geo::HID, Geo::HID};
-    GEMM("heads_l2_wgrad", CfgSmall, al, bl, ep, Geo::HID, Geo::HID, Mb, 2, Mb, 0);
+    GEMM_FFMA("heads_l2_wgrad", CfgSmall, al, bl, ep, Geo::HID, Geo::HID, Mb, 2, Mb, 0);
   }
   {  // dhid1 = dhid2 W2^T * relu'(hid1)
     PlainA al{bw.dhid2, Geo::HID, (size_t)Mb * Geo::HID};
     PlainBT bl{P + pl.actor2_w, Geo::HID, head_stride};
     EpReluMask ep{bw.dhid1, act.hid1, Geo::HID, (size_t)Mb * Geo::HID, (size_t)M * Geo::HID};
-    GEMM("heads_l2_dgrad", CfgSmall, al, bl, ep, Mb, Geo::HID, Geo::HID, 2, Geo::HID, 0);
+    GEMM_FFMA("heads_l2_dgrad", CfgSmall, al, bl, ep, Mb, Geo::HID, Geo::HID, 2, Geo::HID, 0);
   }
   {  // d {actor1, critic1} = h1^T dhid1
     PlainAT al{act.h1, Geo::L, 0};
     PlainB bl{bw.dhid1, Geo::HID, (size_t)Mb * Geo::HID};
     EpRaw<true> ep{G + pl.actor1_w, Geo::HID, head_stride, 1.0f, Geo::L, Geo::HID};
-    GEMM("heads_l1_wgrad", CfgSmall, al, bl, ep, Geo::L, Geo::HID, Mb, 2, Mb, 0);
+    GEMM_FFMA("heads_l1_wgrad", CfgSmall, al, bl, ep, Geo::L, Geo::HID, Mb, 2, Mb, 0);
   }
   {  // dh1 contributions (actor, critic) = dhid1 W1^T ; summed in the gate kernel
     PlainA al{bw.dhid1, Geo::HID, (size_t)Mb * Geo::HID};
     PlainBT bl{P + pl.actor1_w, Geo::HID, head_stride};
     EpRaw<false> ep{bw.dh_part, Geo::L, (size_t)Mb * Geo::L, 1.0f, 0, Geo::L};
-    GEMM("heads_l1_dgrad", CfgSmall, al, bl, ep, Mb, Geo::L, Geo::HID, 2, Geo::HID, 0);
+    GEMM_FFMA("heads_l1_dgrad", CfgSmall, al, bl, ep, Mb, Geo::L, Geo::HID, 2, Geo::HID, 0);
   }
   // ---- LSTM cell ---------------------------------------------------------------------------
   KERNEL("lstm_gates_bwd",
@@ -210,13 +239,13 @@ int net_backward(cudaStream_t s, const ParamLayout& pl, const float* P, float* G
     LstmAT al{act.a3, act.table, in.pa, in.h0, map};
     PlainB bl{bw.dz, Geo::G4, 0};
     EpRaw<true> ep{G + pl.lstm_w, Geo::G4, 0, 1.0f, Geo::XK, Geo::G4};
-    GEMM("lstm_wgrad", CfgBig, al, bl, ep, Geo::XK, Geo::G4, Mb, 1, Mb, 0);
+    GEMM("lstm_wgrad", CfgBig, U128, al, bl, ep, Geo::XK, Geo::G4, Mb, 1, Mb, 0);
   }
   {  // d[a3 | emb] = dz W[:3392]^T  (h0, c0 are fed data: no gradient, agent/impala.py:38-39)
     PlainA al{bw.dz, Geo::G4, 0};
     PlainBT bl{P + pl.lstm_w, Geo::G4, 0};
     EpLstmDx ep{bw.da3, act.a3, bw.du};
-    GEMM("lstm_dgrad", CfgMid, al, bl, ep, Mb, Geo::FLAT + Geo::EMB, Geo::G4, 1, Geo::G4, 0);
+    GEMM("lstm_dgrad", CfgMid, U128, al, bl, ep, Mb, Geo::FLAT + Geo::EMB, Geo::G4, 1, Geo::G4, 0);
   }
   // ---- action embedding --------------------------------------------------------------------
   KERNEL("emb_bwd",
@@ -224,44 +253,44 @@ int net_backward(cudaStream_t s, const ParamLayout& pl, const float* P, float* G
                       G + pl.emb1_b, G + pl.emb2_w, G + pl.emb2_b, Mb, B, T, A), 3);
   // ---- conv3 -------------------------------------------------------------------------------
   {
-    const SplitPlan sp = plan_split(Mb * 49, cdiv(576, CfgBig::BM), 16);
+    const SplitPlan sp = plan_conv3_wgrad(Mb, mode);
     const size_t slab = 577 * 64;
     Conv3WA al{act.a2, map};
     PlainB bl{bw.da3, 64, 0};
     EpRaw<true> ep{bw.wg_part, 64, slab, 1.0f, 576, 64};
-    GEMM("conv3_wgrad", CfgBig, al, bl, ep, 576, 64, Mb * 49, sp.splits, sp.kchunk, sp.kchunk);
+    GEMM("conv3_wgrad", CfgBig, U64, al, bl, ep, 576, 64, Mb * 49, sp.splits, sp.kchunk, sp.kchunk);
     KERNEL("conv3_wgrad_reduce", splitk_reduce(s, bw.wg_part, slab, sp.splits, G + pl.conv3_w, slab), 1);
   }
   {
     Conv3DA al{bw.da3};
     Conv3DB bl{P + pl.conv3_w};
     Conv3DE ep{bw.da2, act.a2};
-    GEMM("conv3_dgrad", CfgBig, al, bl, ep, Mb * 81, 64, 576, 1, 576, 0);
+    GEMM("conv3_dgrad", CfgBig, U64, al, bl, ep, Mb * 81, 64, 576, 1, 576, 0);
   }
   // ---- conv2 -------------------------------------------------------------------------------
   {
-    const SplitPlan sp = plan_split(Mb * 81, cdiv(512, CfgBig::BM), 16);
+    const SplitPlan sp = plan_conv2_wgrad(Mb, mode);
     const size_t slab = 513 * 64;
     Conv2WA al{act.a1, map};
     PlainB bl{bw.da2, 64, 0};
     EpRaw<true> ep{bw.wg_part, 64, slab, 1.0f, 512, 64};
-    GEMM("conv2_wgrad", CfgBig, al, bl, ep, 512, 64, Mb * 81, sp.splits, sp.kchunk, sp.kchunk);
+    GEMM("conv2_wgrad", CfgBig, U64, al, bl, ep, 512, 64, Mb * 81, sp.splits, sp.kchunk, sp.kchunk);
     KERNEL("conv2_wgrad_reduce", splitk_reduce(s, bw.wg_part, slab, sp.splits, G + pl.conv2_w, slab), 1);
   }
   {
     Conv2DA al{bw.da2};
     Conv2DB bl{P + pl.conv2_w};
     Conv2DE ep{bw.da1, act.a1};
-    GEMM("conv2_dgrad", CfgN32, al, bl, ep, Mb * 100, 32, 256, 4, 256, 0);
+    GEMM("conv2_dgrad", CfgN32, U32, al, bl, ep, Mb * 100, 32, 256, 4, 256, 0);
   }
   // ---- conv1 (input is data: weight gradient only) -----------------------------------------
   {
-    const SplitPlan sp = plan_split(Mb * 400, cdiv(256, CfgWg1::BM), 16);
+    const SplitPlan sp = plan_conv1_wgrad(Mb, mode);
     const size_t slab = 257 * 32;
     Conv1WA al{in.frames, map};
     PlainB bl{bw.da1, 32, 0};
     EpRaw<true> ep{bw.wg_part, 32, slab, 1.0f / 255.0f, 256, 32};
-    GEMM("conv1_wgrad", CfgWg1, al, bl, ep, 256, 32, Mb * 400, sp.splits, sp.kchunk, sp.kchunk);
+    GEMM("conv1_wgrad", CfgWg1, U32, al, bl, ep, 256, 32, Mb * 400, sp.splits, sp.kchunk, sp.kchunk);
     KERNEL("conv1_wgrad_reduce", splitk_reduce(s, bw.wg_part, slab, sp.splits, G + pl.conv1_w, slab), 1);
   }
   g_bwd_launches = n;

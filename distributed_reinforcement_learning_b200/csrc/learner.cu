@@ -50,7 +50,7 @@ using namespace drl;
 
 struct drl_learner {
   drl_learner_config cfg{};
-  int B = 0, T = 0, A = 0, M = 0, Mb = 0;
+  int B = 0, T = 0, A = 0, M = 0, Mb = 0, mode = 1;
   ParamLayout pl{};
   cudaStream_t compute = nullptr, copy = nullptr;
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done = nullptr;
@@ -119,7 +119,7 @@ int download_flat(drl_learner* h, const float* dev_padded, float* host_packed) {
 }
 
 int enqueue_forward(drl_learner* h, const Inputs& in, int B, int T) {
-  return net_forward(h->compute, h->pl, h->params, in, h->act, B, T);
+  return net_forward(h->compute, h->pl, h->params, in, h->act, B, T, h->mode);
 }
 
 int enqueue_forward_backward(drl_learner* h, int slot) {
@@ -129,7 +129,7 @@ int enqueue_forward_backward(drl_learner* h, int slot) {
   prof_mark(h->compute, "vtrace_losses");
   DRL_TRY(vtrace_losses(h->compute, vc, h->act.policy, h->act.value, in, h->vt, h->bwd.dlogits, h->bwd.dv, h->B,
                         h->T, h->A));
-  DRL_TRY(net_backward(h->compute, h->pl, h->params, h->bucket, in, h->act, h->bwd, h->B, h->T));
+  DRL_TRY(net_backward(h->compute, h->pl, h->params, h->bucket, in, h->act, h->bwd, h->B, h->T, h->mode));
   return DRL_OK;
 }
 
@@ -219,11 +219,12 @@ int drl_learner_create(const drl_learner_config* cfg, drl_learner** out) {
     set_error("reward_clipping must be DRL_REWARD_ABS_ONE or DRL_REWARD_SOFT_ASYMMETRIC");   // utils.py:45
     return DRL_ERR_INVALID;
   }
-  if (cfg->math_mode != 0 && cfg->math_mode != 1) { set_error("math_mode %d not available in this build", cfg->math_mode); return DRL_ERR_INVALID; }
+  if (cfg->math_mode < 0 || cfg->math_mode > 2) { set_error("math_mode must be 0 (default), 1 (FP32 FFMA) or 2 (tcgen05 3xTF32)"); return DRL_ERR_INVALID; }
   if (drl_device_count() <= cfg->device) { set_error("CUDA device %d not available (no CPU fallback)", cfg->device); return DRL_ERR_CUDA; }
 
   drl_learner* h = new drl_learner();
   h->cfg = *cfg;
+  h->mode = (cfg->math_mode == 0) ? DRL_DEFAULT_MATH_MODE : cfg->math_mode;
   if (h->cfg.num_slots < 1) h->cfg.num_slots = 2;
   h->B = cfg->batch; h->T = cfg->trajectory; h->A = cfg->num_action;
   h->M = h->B * h->T; h->Mb = h->B * (h->T - 2);

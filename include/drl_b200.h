@@ -149,6 +149,12 @@ int drl_learner_act(drl_learner* h, int32_t n, const uint8_t* state, const int32
  * '\n'-joined list (names_len bytes available), ms[i] the time from launch i to launch i+1. */
 int drl_learner_profile_step(drl_learner* h, int32_t slot, char* names, int64_t names_len, float* ms,
                              int32_t max_kernels, int32_t* count);
+/* Test aid: one plain GEMM C[M,N] = A*B on a chosen contraction core (1 = FP32 FFMA, 2 = tcgen05 3xTF32) and
+ * operand-major combination, to validate shared-memory layouts / UMMA descriptors in isolation.
+ * a_kmajor: A is [M,K] row-major (1) or [K,M] row-major (0); b_kmajor: B is [N,K] (1) or [K,N] (0).
+ * C: `splits` slabs of [(M+1), N] floats (split-K partials; row M = column sums of B for N-major B). */
+int drl_debug_gemm(int32_t core, int32_t bn, int32_t a_kmajor, int32_t b_kmajor, int32_t M, int32_t N,
+                   int32_t K, int32_t splits, const float* A, const float* B, float* C);
 /* Device-time of the last step's compute (CUDA events on the compute stream), milliseconds. */
 int drl_learner_last_step_ms(drl_learner* h, float* ms);
 /* Number of kernel launches one step issues (for bench.py's gpu_launches claim). */
