@@ -19,9 +19,9 @@ static int run_one(int core, int bn, cudaStream_t s, const AL& al, const BL& bl,
   EpRaw<true> ep{C, N, (size_t)(M + 1) * N, 1.0f, M, N};     // slab z: [M+1, N], row M = column sums of B
   if (core == 1) return launch_gemm_simt<CfgMid>(s, al, bl, ep, M, N, K, nz, kchunk, kchunk);
   switch (bn) {
-    case 32: return launch_gemm_umma<UmmaCfg<32, 4>>(s, al, bl, ep, M, N, K, nz, kchunk, kchunk);
-    case 64: return launch_gemm_umma<UmmaCfg<64, 4>>(s, al, bl, ep, M, N, K, nz, kchunk, kchunk);
-    case 128: return launch_gemm_umma<UmmaCfg<128, 3>>(s, al, bl, ep, M, N, K, nz, kchunk, kchunk);
+    case 32: return launch_gemm_umma<UmmaCfg<32, 2, 2>>(s, al, bl, ep, M, N, K, nz, kchunk, kchunk);
+    case 64: return launch_gemm_umma<UmmaCfg<64, 2, 2>>(s, al, bl, ep, M, N, K, nz, kchunk, kchunk);
+    case 128: return launch_gemm_umma<UmmaCfg<128, 3, 1>>(s, al, bl, ep, M, N, K, nz, kchunk, kchunk);
     default: set_error("debug_gemm: bn must be 32, 64 or 128"); return DRL_ERR_INVALID;
   }
 }

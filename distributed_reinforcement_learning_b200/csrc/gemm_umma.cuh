@@ -27,6 +27,8 @@
 //   MN-major: SWIZZLE_128B_BASE32B, atoms of 32 (mn) x 4 (k) -- see UmmaTile below.
 // All operand tiles are 1024-byte aligned (base_offset = 0).
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace drl {
@@ -162,37 +164,48 @@ struct UmmaTile {
   __device__ static __forceinline__ int kslice_off(int j) { return KMAJOR ? j * 32 : j * 2 * SBO; }
 };
 
-template <int BN_, int STAGES_>
+template <int BN_, int STAGES_, int MINB_ = 1>
 struct UmmaCfg {
-  static constexpr int BM = 128, BN = BN_, BK = 32, STAGES = STAGES_;
+  static constexpr int BM = 128, BN = BN_, BK = 32, STAGES = STAGES_, MINB = MINB_;
   static constexpr int NPROD = 128;     // producer / epilogue threads (warps 0-3)
   static constexpr int NT = 160;        // + MMA warp
   static constexpr int TMEM_COLS = BN;
   static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 256, "BN must be a power of two in [32,256]");
 };
 
+// A loader may declare `static constexpr bool kExactTf32 = true` when its values are exactly representable in
+// tf32 (the uint8 frame bytes): then lo == 0, the lo tile is not written and the A_lo*B_hi product is skipped
+// ("2xTF32").
+template <class L, class = void>
+struct loader_exact : std::false_type {};
+template <class L>
+struct loader_exact<L, std::void_t<decltype(L::kExactTf32)>> : std::bool_constant<L::kExactTf32> {};
+
 template <class Cfg, class AL, class BL>
 struct UmmaSmem {
   using TA = UmmaTile<Cfg::BM, AL::kContigK>;
   using TB = UmmaTile<Cfg::BN, BL::kContigK>;
+  static constexpr bool AEX = loader_exact<AL>::value;
   static constexpr int A_BYTES = TA::BYTES, B_BYTES = TB::BYTES;       // multiples of 1024
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;        // hi and lo copies of both operands
+  static constexpr int STAGE_BYTES = (AEX ? 1 : 2) * A_BYTES + 2 * B_BYTES;   // hi (and lo) copies of the operands
   static constexpr int AUX_BYTES = 1024 + (BL::kContigK ? 0 : Cfg::NPROD * 16);   // barriers, tmem ptr, colsum scratch
   static constexpr int BYTES = Cfg::STAGES * STAGE_BYTES + AUX_BYTES + 1024;      // + alignment slack
 };
 
 template <class Cfg, class AL, class BL, class EP>
-__global__ void __launch_bounds__(Cfg::NT, 1)
+__global__ void __launch_bounds__(Cfg::NT, Cfg::MINB)
 gemm_umma_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, int kchunk, int kstep) {
   constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES, NPROD = Cfg::NPROD;
   constexpr bool AK = AL::kContigK, BKc = BL::kContigK;
   using SM = UmmaSmem<Cfg, AL, BL>;
   using TA = typename SM::TA;
   using TB = typename SM::TB;
+  constexpr bool AEX = SM::AEX;
   constexpr int NGA = BM * BK / 4, NGB = BN * BK / 4;       // float4 groups per stage
   constexpr int GA = NGA / NPROD, GB = NGB / NPROD;          // per producer thread (8 and BN/16)
   static_assert(NGA % NPROD == 0 && NGB % NPROD == 0, "groups must divide among producers");
   constexpr bool kColSum = EP::kColSum && !BKc;
+  constexpr int OFF_ALO = SM::A_BYTES, OFF_BHI = (AEX ? 1 : 2) * SM::A_BYTES, OFF_BLO = OFF_BHI + SM::B_BYTES;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -267,11 +280,9 @@ gemm_umma_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, int
 #pragma unroll
     for (int i = 0; i < GB; ++i) csum[i] = zero4();
 
-    for (int t = 0; t < ntiles; ++t) {
-      const int s = t % STAGES;
-      const uint32_t ph = (t / STAGES) & 1;
+    // gather tile t into registers
+    auto gload = [&](int t, float4 (&ra)[GA], float4 (&rb)[GB]) {
       const int kb = k0 + t * BK;
-      float4 ra[GA], rb[GB];          // global loads are issued before waiting for the slot
 #pragma unroll
       for (int i = 0; i < GA; ++i) {
         const int k = kb + a_k[i];
@@ -281,30 +292,48 @@ gemm_umma_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, int
       for (int i = 0; i < GB; ++i) {
         const int k = kb + b_k[i];
         rb[i] = (k < k1) ? bl.load(brow[i], k) : zero4();
-        if (kColSum) { csum[i].x += rb[i].x; csum[i].y += rb[i].y; csum[i].z += rb[i].z; csum[i].w += rb[i].w; }
       }
+    };
+    // split tile t into hi/lo and publish it in its shared-memory stage
+    auto publish = [&](int t, const float4 (&ra)[GA], const float4 (&rb)[GB]) {
+      const int s = t % STAGES;
+      const uint32_t ph = (t / STAGES) & 1;
       umma::mbar_wait(&empty[s], ph ^ 1);
       uint8_t* st = smem + s * SM::STAGE_BYTES;
-      uint8_t* a_hi = st;
-      uint8_t* a_lo = st + SM::A_BYTES;
-      uint8_t* b_hi = st + 2 * SM::A_BYTES;
-      uint8_t* b_lo = b_hi + SM::B_BYTES;
 #pragma unroll
       for (int i = 0; i < GA; ++i) {
-        float4 h, l;
-        umma::split4(ra[i], h, l);
-        *reinterpret_cast<float4*>(a_hi + a_o[i]) = h;
-        *reinterpret_cast<float4*>(a_lo + a_o[i]) = l;
+        if (AEX) {
+          *reinterpret_cast<float4*>(st + a_o[i]) = ra[i];
+        } else {
+          float4 h, l;
+          umma::split4(ra[i], h, l);
+          *reinterpret_cast<float4*>(st + a_o[i]) = h;
+          *reinterpret_cast<float4*>(st + OFF_ALO + a_o[i]) = l;
+        }
       }
 #pragma unroll
       for (int i = 0; i < GB; ++i) {
         float4 h, l;
         umma::split4(rb[i], h, l);
-        *reinterpret_cast<float4*>(b_hi + b_o[i]) = h;
-        *reinterpret_cast<float4*>(b_lo + b_o[i]) = l;
+        *reinterpret_cast<float4*>(st + OFF_BHI + b_o[i]) = h;
+        *reinterpret_cast<float4*>(st + OFF_BLO + b_o[i]) = l;
+        if (kColSum) { csum[i].x += rb[i].x; csum[i].y += rb[i].y; csum[i].z += rb[i].z; csum[i].w += rb[i].w; }
       }
       umma::fence_proxy_async();       // generic-proxy writes -> visible to the tensor-core (async) proxy
       umma::mbar_arrive(&full[s]);
+    };
+
+    // register double buffering: the gathers of tile t+1 are in flight while tile t is split and stored
+    float4 ra0[GA], rb0[GB], ra1[GA], rb1[GB];
+    if (ntiles > 0) gload(0, ra0, rb0);
+#pragma unroll 1
+    for (int t = 0; t < ntiles; t += 2) {
+      if (t + 1 < ntiles) gload(t + 1, ra1, rb1);
+      publish(t, ra0, rb0);
+      if (t + 1 < ntiles) {
+        if (t + 2 < ntiles) gload(t + 2, ra0, rb0);
+        publish(t + 1, ra1, rb1);
+      }
     }
 
     // bias-gradient row: column sums of B (dY) over this CTA's K range, reduced in fixed order
@@ -366,16 +395,21 @@ gemm_umma_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, int
       umma::tc_fence_after();
       if (lane == 0) {
         const uint32_t st = umma::smem_u32(smem + s * SM::STAGE_BYTES);
-        const uint32_t a_hi = st, a_lo = st + SM::A_BYTES, b_hi = st + 2 * SM::A_BYTES, b_lo = b_hi + SM::B_BYTES;
+        const uint32_t a_hi = st, a_lo = st + OFF_ALO, b_hi = st + OFF_BHI, b_lo = st + OFF_BLO;
 #pragma unroll
         for (int j = 0; j < BK / 8; ++j) {
           const uint32_t ao = TA::kslice_off(j), bo = TB::kslice_off(j);
           const uint64_t dah = umma::make_desc(a_hi + ao, TA::LBO, TA::SBO, TA::LAYOUT_TYPE);
-          const uint64_t dal = umma::make_desc(a_lo + ao, TA::LBO, TA::SBO, TA::LAYOUT_TYPE);
           const uint64_t dbh = umma::make_desc(b_hi + bo, TB::LBO, TB::SBO, TB::LAYOUT_TYPE);
           const uint64_t dbl = umma::make_desc(b_lo + bo, TB::LBO, TB::SBO, TB::LAYOUT_TYPE);
-          umma::mma_tf32(tmem_base, dal, dbh, idesc, (t > 0 || j > 0) ? 1u : 0u);   // small terms first
-          umma::mma_tf32(tmem_base, dah, dbl, idesc, 1u);
+          const uint32_t first = (t > 0 || j > 0) ? 1u : 0u;
+          if (!AEX) {                                                    // small terms first
+            const uint64_t dal = umma::make_desc(a_lo + ao, TA::LBO, TA::SBO, TA::LAYOUT_TYPE);
+            umma::mma_tf32(tmem_base, dal, dbh, idesc, first);
+            umma::mma_tf32(tmem_base, dah, dbl, idesc, 1u);
+          } else {
+            umma::mma_tf32(tmem_base, dah, dbl, idesc, first);
+          }
           umma::mma_tf32(tmem_base, dah, dbh, idesc, 1u);
         }
         umma::mma_commit(&empty[s]);            // frees the smem slot once these MMAs have read it

@@ -55,9 +55,9 @@ using Conv2DA = ConvDgradA<9, 9, 64, 2, 4, 4, 10, 10>;
 using Conv2DB = ConvDgradB<32, 64, 2, 4, 4>;
 using Conv2DE = EpConvDx<20, 20, 32, 2, 10, 10>;
 
-using U32 = UmmaCfg<32, 4>;     // 40 KB / stage
-using U64 = UmmaCfg<64, 4>;     // 48 KB / stage
-using U128 = UmmaCfg<128, 3>;   // 64 KB / stage
+using U32 = UmmaCfg<32, 2, 2>;   // 40 KB / stage (24 KB when A is exact), 2 CTAs per SM
+using U64 = UmmaCfg<64, 2, 2>;   // 48 KB / stage, 2 CTAs per SM
+using U128 = UmmaCfg<128, 3, 1>; // 64 KB / stage, 1 CTA per SM
 
 static int g_fwd_launches = 0, g_bwd_launches = 0;
 int forward_launch_count() { return g_fwd_launches; }
@@ -100,15 +100,15 @@ static SplitPlan plan_split(int K, int tiles_mn, int bk, int waves) {
   p.splits = (K + kchunk - 1) / kchunk;
   return p;
 }
-// the conv weight-gradient plans (mode 1: FFMA tiles, 2 waves; mode 2: 128-row UMMA tiles, 1 CTA/SM)
+// the conv weight-gradient plans (mode 1: FFMA tiles, 2 waves; mode 2: 128-row UMMA tiles, 2 CTAs/SM)
 static SplitPlan plan_conv1_wgrad(int Mb, int mode) {
-  return mode == 2 ? plan_split(Mb * 400, 2, 32, 1) : plan_split(Mb * 400, cdiv(256, CfgWg1::BM), 16, 2);
+  return mode == 2 ? plan_split(Mb * 400, 2, 32, 2) : plan_split(Mb * 400, cdiv(256, CfgWg1::BM), 16, 2);
 }
 static SplitPlan plan_conv2_wgrad(int Mb, int mode) {
-  return mode == 2 ? plan_split(Mb * 81, 4, 32, 1) : plan_split(Mb * 81, cdiv(512, CfgBig::BM), 16, 2);
+  return mode == 2 ? plan_split(Mb * 81, 4, 32, 2) : plan_split(Mb * 81, cdiv(512, CfgBig::BM), 16, 2);
 }
 static SplitPlan plan_conv3_wgrad(int Mb, int mode) {
-  return mode == 2 ? plan_split(Mb * 49, 5, 32, 1) : plan_split(Mb * 49, cdiv(576, CfgBig::BM), 16, 2);
+  return mode == 2 ? plan_split(Mb * 49, 5, 32, 2) : plan_split(Mb * 49, cdiv(576, CfgBig::BM), 16, 2);
 }
 
 size_t wgrad_partial_floats(int B, int T) {

@@ -30,6 +30,7 @@ struct RowMap {
 template <typename T, int IH, int IW, int C, int OH, int OW, int KW, int S, bool REMAP>
 struct ConvFwdA {
   static constexpr bool kContigK = true;
+  static constexpr bool kExactTf32 = (sizeof(T) == 1);   // uint8 frame bytes are exact in tf32
   const T* x;
   RowMap map;
   struct Row { const T* base; };
@@ -61,6 +62,7 @@ struct ConvFwdA {
 template <typename T, int IH, int IW, int C, int OH, int OW, int KW, int S, bool REMAP>
 struct ConvWgradA {
   static constexpr bool kContigK = false;
+  static constexpr bool kExactTf32 = (sizeof(T) == 1);
   const T* x;
   RowMap map;
   struct Row { int off; };
