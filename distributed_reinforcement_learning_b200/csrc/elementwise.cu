@@ -11,26 +11,38 @@ namespace drl {
 // action_embedding (model/impala_actor_critic.py:12-16) evaluated once per distinct action:
 //   e1[a]    = relu(W1[a,:] + b1)            (one_hot(a) @ W1 is row a of W1)
 //   table[a] = relu(e1[a] @ W2 + b2)
-// grid = A blocks, 256 threads (one output column each)
+// grid = (A, 4): a block owns 64 output columns of one action; its 256 threads = 64 columns x 4 K slices
+// (the 256-long dot products are latency-bound, so the reduction is split and combined through shared memory)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) emb_forward_kernel(const float* __restrict__ w1, const float* __restrict__ b1,
                                                            const float* __restrict__ w2, const float* __restrict__ b2,
                                                            float* __restrict__ e1, float* __restrict__ table) {
   __shared__ float se[Geo::EMB];
-  const int a = blockIdx.x, j = threadIdx.x;
-  const float v = fmaxf(w1[a * Geo::EMB + j] + b1[j], 0.f);
-  se[j] = v;
-  e1[a * Geo::EMB + j] = v;
+  __shared__ float part[4][64];
+  const int a = blockIdx.x, tid = threadIdx.x;
+  const float v = fmaxf(w1[a * Geo::EMB + tid] + b1[tid], 0.f);
+  se[tid] = v;
+  if (blockIdx.y == 0) e1[a * Geo::EMB + tid] = v;
   __syncthreads();
-  float acc = 0.f;
+  const int c = tid & 63, ks = tid >> 6;
+  const int j = blockIdx.y * 64 + c;
+  float acc0 = 0.f, acc1 = 0.f;
 #pragma unroll 8
-  for (int k = 0; k < Geo::EMB; ++k) acc = fmaf(se[k], __ldg(w2 + k * Geo::EMB + j), acc);
-  table[a * Geo::EMB + j] = fmaxf(acc + b2[j], 0.f);
+  for (int k = ks * 64; k < ks * 64 + 64; k += 2) {
+    acc0 = fmaf(se[k], __ldg(w2 + k * Geo::EMB + j), acc0);
+    acc1 = fmaf(se[k + 1], __ldg(w2 + (k + 1) * Geo::EMB + j), acc1);
+  }
+  part[ks][c] = acc0 + acc1;
+  __syncthreads();
+  if (tid < 64) {
+    const float s = (part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]);
+    table[a * Geo::EMB + j] = fmaxf(s + b2[j], 0.f);
+  }
 }
 
 int emb_forward(cudaStream_t s, const float* w1, const float* b1, const float* w2, const float* b2, float* e1,
                 float* table, int A) {
-  emb_forward_kernel<<<A, 256, 0, s>>>(w1, b1, w2, b2, e1, table);
+  emb_forward_kernel<<<dim3(A, 4), 256, 0, s>>>(w1, b1, w2, b2, e1, table);
   DRL_CHECK_LAUNCH();
   return DRL_OK;
 }
@@ -195,16 +207,27 @@ int heads_out_backward(cudaStream_t s, const float* dlogits, const float* dv, co
 // the per-row gradients are first summed per action (segment sum) and then pushed through the
 // A-row MLP once (linear in the upstream gradient, so this equals the per-row backward summed).
 // ------------------------------------------------------------------------------------------
-// (1) dpre2[a,j] = relu'(table[a,j]) * sum_{m<Mb, pa[m]==a} du[m,j]      grid A, 256 threads
+// (1a) part[c][a][j] = sum_{m in row chunk c, pa[m]==a} du[m,j]                       grid (A, kEmbChunks), 256 threads
+constexpr int kEmbChunks = 16;
 __global__ void __launch_bounds__(256) emb_segsum_kernel(const float* __restrict__ du, const int32_t* __restrict__ pa,
-                                                          const float* __restrict__ table,
-                                                          float* __restrict__ dpre2, int Mb, int B, int T) {
-  const int a = blockIdx.x, j = threadIdx.x;
+                                                          float* __restrict__ part, int Mb, int B, int T, int A) {
+  const int a = blockIdx.x, c = blockIdx.y, j = threadIdx.x;
+  const int per = (Mb + kEmbChunks - 1) / kEmbChunks;
+  const int lo = c * per, hi = min(Mb, lo + per);
   float acc = 0.f;
-  for (int m = 0; m < Mb; ++m) {
+  for (int m = lo; m < hi; ++m) {
     const int t = m / B, b = m - t * B;
     if (__ldg(pa + b * T + t) == a) acc += du[(size_t)m * Geo::EMB + j];
   }
+  part[((size_t)c * A + a) * Geo::EMB + j] = acc;
+}
+// (1b) dpre2[a,j] = relu'(table[a,j]) * sum_c part[c][a][j]   (fixed order)           grid A, 256 threads
+__global__ void __launch_bounds__(256) emb_dpre2_kernel(const float* __restrict__ part, const float* __restrict__ table,
+                                                         float* __restrict__ dpre2, int A) {
+  const int a = blockIdx.x, j = threadIdx.x;
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < kEmbChunks; ++c) acc += part[((size_t)c * A + a) * Geo::EMB + j];
   dpre2[a * Geo::EMB + j] = (table[a * Geo::EMB + j] > 0.f) ? acc : 0.f;
 }
 // (2) g_w2[k,j] = sum_a e1[a,k] dpre2[a,j] ; g_b2[j] = sum_a dpre2[a,j]             grid 256 (k), 256 threads (j)
@@ -248,8 +271,11 @@ __global__ void __launch_bounds__(256) emb_bwd1_kernel(const float* __restrict__
 
 int emb_backward(cudaStream_t s, const float* du, const int32_t* pa, const float* e1, const float* table,
                  const float* w2, float* dpre2, float* dpre1, float* g_w1, float* g_b1, float* g_w2, float* g_b2,
-                 int Mb, int B, int T, int A) {
-  emb_segsum_kernel<<<A, 256, 0, s>>>(du, pa, table, dpre2, Mb, B, T);
+                 float* scratch, int Mb, int B, int T, int A) {
+  // scratch: >= kEmbChunks * A * 256 floats (the split-K partial buffer, idle at this point of the step)
+  emb_segsum_kernel<<<dim3(A, kEmbChunks), 256, 0, s>>>(du, pa, scratch, Mb, B, T, A);
+  DRL_CHECK_LAUNCH();
+  emb_dpre2_kernel<<<A, 256, 0, s>>>(scratch, table, dpre2, A);
   DRL_CHECK_LAUNCH();
   emb_bwd2_kernel<<<Geo::EMB, 256, 0, s>>>(e1, dpre2, g_w2, g_b2, A);
   DRL_CHECK_LAUNCH();

@@ -263,7 +263,7 @@ inline int launch_gemm_simt(cudaStream_t s, const AL& al, const BL& bl, const EP
 using CfgBig = TileCfg<128, 64, 16, 8, 8>;    // 128 threads, 64 accumulators
 using CfgN32 = TileCfg<128, 32, 16, 8, 4>;    // N = 32 outputs (conv1, conv2-dgrad)
 using CfgMid = TileCfg<64, 64, 16, 8, 4>;     // 128 threads, small-M GEMMs (LSTM, dgrads)
-using CfgSmall = TileCfg<32, 64, 16, 4, 4>;   // 128 threads, tiny dense layers
+using CfgSmall = TileCfg<32, 64, 64, 4, 4>;   // 128 threads, tiny dense layers: latency-bound, so few deep K tiles
 using CfgWg1 = TileCfg<256, 32, 16, 8, 8>;    // conv1 wgrad: C is [256(+1) x 32]
 
 }  // namespace drl

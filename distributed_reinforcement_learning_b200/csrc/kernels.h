@@ -113,7 +113,7 @@ int lstm_gates_backward(cudaStream_t s, const float* dh_part, size_t part_stride
                         const float* tc1, const float* c0, float* dz, int Mb, int B, int T);
 int emb_backward(cudaStream_t s, const float* du, const int32_t* pa, const float* e1, const float* table,
                  const float* w2, float* dpre2, float* dpre1, float* g_w1, float* g_b1, float* g_w2, float* g_b2,
-                 int Mb, int B, int T, int A);
+                 float* scratch, int Mb, int B, int T, int A);
 int splitk_reduce(cudaStream_t s, const float* part, size_t slab, int nsplit, float* out, size_t n);
 
 // ---- vtrace.cu ----------------------------------------------------------------------------

@@ -119,7 +119,7 @@ size_t wgrad_partial_floats(int B, int T) {
     mx = std::max(mx, (size_t)plan_conv2_wgrad(Mb, mode).splits * 513 * 64);
     mx = std::max(mx, (size_t)plan_conv3_wgrad(Mb, mode).splits * 577 * 64);
   }
-  return mx;
+  return std::max(mx, (size_t)16 * 32 * 256);   // also the scratch of emb_backward (kEmbChunks * A * 256)
 }
 
 int net_forward(cudaStream_t s, const ParamLayout& pl, const float* P, const Inputs& in, const Acts& act, int B,
@@ -250,7 +250,7 @@ int net_backward(cudaStream_t s, const ParamLayout& pl, const float* P, float* G
   // ---- action embedding --------------------------------------------------------------------
   KERNEL("emb_bwd",
          emb_backward(s, bw.du, in.pa, act.e1, act.table, P + pl.emb2_w, bw.dpre2, bw.dpre1, G + pl.emb1_w,
-                      G + pl.emb1_b, G + pl.emb2_w, G + pl.emb2_b, Mb, B, T, A), 3);
+                      G + pl.emb1_b, G + pl.emb2_w, G + pl.emb2_b, bw.wg_part, Mb, B, T, A), 4);
   // ---- conv3 -------------------------------------------------------------------------------
   {
     const SplitPlan sp = plan_conv3_wgrad(Mb, mode);
