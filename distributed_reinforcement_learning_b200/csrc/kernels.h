@@ -66,7 +66,8 @@ struct Bwd {             // backward workspace, Mb = B*(T-2) rows
   float* dpre1;          // [A,256]
   float* da2;            // [Mb,9,9,64]
   float* da1;            // [Mb,20,20,32]
-  float* wg_part;        // split-K partial slabs for the conv weight gradients
+  float* wg_part;        // split-K partial slabs for the conv3/conv2 weight gradients (side stream) + emb scratch
+  float* wg_part2;       // split-K partial slabs for the conv1 weight gradient (main stream)
   size_t wg_part_floats;
 };
 
@@ -89,10 +90,17 @@ constexpr int kLstmSplits = 4;
 void prof_mark(cudaStream_t s, const char* name);
 
 // ---- layers.cu ----------------------------------------------------------------------------
+// main = critical path; side = kernels off the critical path (fork/join through ev[]); par = false runs
+// everything on main (used by the per-kernel profile so that event times are per-kernel).
+struct Streams {
+  cudaStream_t main, side;
+  cudaEvent_t ev[8];
+  bool par;
+};
 // mode: 1 = FP32-FFMA gather-GEMM, 2 = tcgen05 3xTF32 gather-GEMM for the large contractions
-int net_forward(cudaStream_t s, const ParamLayout& pl, const float* params, const Inputs& in, const Acts& act,
+int net_forward(const Streams& st, const ParamLayout& pl, const float* params, const Inputs& in, const Acts& act,
                 int B, int T, int mode);
-int net_backward(cudaStream_t s, const ParamLayout& pl, const float* params, float* grads, const Inputs& in,
+int net_backward(const Streams& st, const ParamLayout& pl, const float* params, float* grads, const Inputs& in,
                  const Acts& act, const Bwd& bwd, int B, int T, int mode);
 size_t wgrad_partial_floats(int B, int T);
 int forward_launch_count();

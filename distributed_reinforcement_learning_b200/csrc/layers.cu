@@ -122,11 +122,35 @@ size_t wgrad_partial_floats(int B, int T) {
   return std::max(mx, (size_t)16 * 32 * 256);   // also the scratch of emb_backward (kEmbChunks * A * 256)
 }
 
-int net_forward(cudaStream_t s, const ParamLayout& pl, const float* P, const Inputs& in, const Acts& act, int B,
+// Fork/join helpers: kernels that are off the critical path (the action-embedding table in the forward, every
+// weight gradient except conv1's in the backward) run on the side stream so they fill SMs the critical
+// dgrad chain leaves idle.  Inside CUDA-graph capture the event record/wait pairs become graph edges.
+static int fork_to_side(const Streams& st, int i) {
+  if (!st.par) return DRL_OK;
+  DRL_CUDA_CHECK(cudaEventRecord(st.ev[i], st.main));
+  DRL_CUDA_CHECK(cudaStreamWaitEvent(st.side, st.ev[i], 0));
+  return DRL_OK;
+}
+static int join_from_side(const Streams& st, int i) {
+  if (!st.par) return DRL_OK;
+  DRL_CUDA_CHECK(cudaEventRecord(st.ev[i], st.side));
+  DRL_CUDA_CHECK(cudaStreamWaitEvent(st.main, st.ev[i], 0));
+  return DRL_OK;
+}
+
+int net_forward(const Streams& st, const ParamLayout& pl, const float* P, const Inputs& in, const Acts& act, int B,
                 int T, int mode) {
   const int M = B * T;
   const RowMap map{B, T};
   int n = 0;
+  cudaStream_t s = st.main;
+  const cudaStream_t side = st.par ? st.side : st.main;
+  // action embedding table (:12-16): only A distinct inputs exist; depends on parameters only -> side stream
+  DRL_TRY(fork_to_side(st, 0));
+  s = side;
+  KERNEL("emb_fwd",
+         emb_forward(s, P + pl.emb1_w, P + pl.emb1_b, P + pl.emb2_w, P + pl.emb2_b, act.e1, act.table, pl.A), 1);
+  s = st.main;
   // conv1: u8 frames -> a1 [M,20,20,32]   (attention_CNN, model/impala_actor_critic.py:6)
   {
     Conv1A al{in.frames, map};
@@ -148,9 +172,7 @@ int net_forward(cudaStream_t s, const ParamLayout& pl, const float* P, const Inp
     EpBiasAct<true, true> ep{act.a3, 64, 0, P + pl.conv3_b, 0, 1.0f};
     GEMM("conv3_fwd", CfgBig, U64, al, bl, ep, M * 49, 64, 576, 1, 576, 0);
   }
-  // action embedding table (:12-16): only A distinct inputs exist
-  KERNEL("emb_fwd",
-         emb_forward(s, P + pl.emb1_w, P + pl.emb1_b, P + pl.emb2_w, P + pl.emb2_b, act.e1, act.table, pl.A), 1);
+  DRL_TRY(join_from_side(st, 1));
   // LSTM pre-activation z = [a3 | emb | h0] W  (split-K partial sums; bias added in the gate kernel) (:18-25)
   {
     LstmA al{act.a3, act.table, in.pa, in.h0, map};
@@ -183,8 +205,10 @@ int net_forward(cudaStream_t s, const ParamLayout& pl, const float* P, const Inp
   return DRL_OK;
 }
 
-int net_backward(cudaStream_t s, const ParamLayout& pl, const float* P, float* G, const Inputs& in, const Acts& act,
+int net_backward(const Streams& st, const ParamLayout& pl, const float* P, float* G, const Inputs& in, const Acts& act,
                  const Bwd& bw, int B, int T, int mode) {
+  cudaStream_t s = st.main;
+  const cudaStream_t side = st.par ? st.side : st.main;
   const int M = B * T;
   const int Mb = B * (T - 2);   // rows t <= T-3 are the contiguous prefix (time-major)
   const RowMap map{B, T};
@@ -196,6 +220,8 @@ int net_backward(cudaStream_t s, const ParamLayout& pl, const float* P, float* G
   KERNEL("heads_out_bwd",
          heads_out_backward(s, bw.dlogits, bw.dv, P + pl.actor3_w, P + pl.critic3_w, act.hid2,
                             act.hid2 + (size_t)M * Geo::HID, bw.dhid2, bw.dhid2 + (size_t)Mb * Geo::HID, Mb, A), 1);
+  DRL_TRY(fork_to_side(st, 0));     // dlogits / dv / dhid2 are ready: three weight gradients can start beside the chain
+  s = side;
   {  // d actor3 [256(+1), A]
     PlainAT al{act.hid2, Geo::HID, 0};
     PlainB bl{bw.dlogits, 32, 0};
@@ -214,18 +240,22 @@ int net_backward(cudaStream_t s, const ParamLayout& pl, const float* P, float* G
     EpRaw<true> ep{G + pl.actor2_w, Geo::HID, head_stride, 1.0f, Geo::HID, Geo::HID};
     GEMM_FFMA("heads_l2_wgrad", CfgSmall, al, bl, ep, Geo::HID, Geo::HID, Mb, 2, Mb, 0);
   }
+  s = st.main;
   {  // dhid1 = dhid2 W2^T * relu'(hid1)
     PlainA al{bw.dhid2, Geo::HID, (size_t)Mb * Geo::HID};
     PlainBT bl{P + pl.actor2_w, Geo::HID, head_stride};
     EpReluMask ep{bw.dhid1, act.hid1, Geo::HID, (size_t)Mb * Geo::HID, (size_t)M * Geo::HID};
     GEMM_FFMA("heads_l2_dgrad", CfgSmall, al, bl, ep, Mb, Geo::HID, Geo::HID, 2, Geo::HID, 0);
   }
+  DRL_TRY(fork_to_side(st, 2));
+  s = side;
   {  // d {actor1, critic1} = h1^T dhid1
     PlainAT al{act.h1, Geo::L, 0};
     PlainB bl{bw.dhid1, Geo::HID, (size_t)Mb * Geo::HID};
     EpRaw<true> ep{G + pl.actor1_w, Geo::HID, head_stride, 1.0f, Geo::L, Geo::HID};
     GEMM_FFMA("heads_l1_wgrad", CfgSmall, al, bl, ep, Geo::L, Geo::HID, Mb, 2, Mb, 0);
   }
+  s = st.main;
   {  // dh1 contributions (actor, critic) = dhid1 W1^T ; summed in the gate kernel
     PlainA al{bw.dhid1, Geo::HID, (size_t)Mb * Geo::HID};
     PlainBT bl{P + pl.actor1_w, Geo::HID, head_stride};
@@ -235,19 +265,24 @@ int net_backward(cudaStream_t s, const ParamLayout& pl, const float* P, float* G
   // ---- LSTM cell ---------------------------------------------------------------------------
   KERNEL("lstm_gates_bwd",
          lstm_gates_backward(s, bw.dh_part, (size_t)Mb * Geo::L, act.gates, act.tc1, in.c0, bw.dz, Mb, B, T), 1);
+  DRL_TRY(fork_to_side(st, 3));
+  s = side;
   {  // d lstm kernel [3648(+1), 1024] = x^T dz ; bias gradient = column sums of dz
     LstmAT al{act.a3, act.table, in.pa, in.h0, map};
     PlainB bl{bw.dz, Geo::G4, 0};
     EpRaw<true> ep{G + pl.lstm_w, Geo::G4, 0, 1.0f, Geo::XK, Geo::G4};
     GEMM("lstm_wgrad", CfgBig, U128, al, bl, ep, Geo::XK, Geo::G4, Mb, 1, Mb, 0);
   }
+  s = st.main;
   {  // d[a3 | emb] = dz W[:3392]^T  (h0, c0 are fed data: no gradient, agent/impala.py:38-39)
     PlainA al{bw.dz, Geo::G4, 0};
     PlainBT bl{P + pl.lstm_w, Geo::G4, 0};
     EpLstmDx ep{bw.da3, act.a3, bw.du};
     GEMM("lstm_dgrad", CfgMid, U128, al, bl, ep, Mb, Geo::FLAT + Geo::EMB, Geo::G4, 1, Geo::G4, 0);
   }
-  // ---- action embedding --------------------------------------------------------------------
+  // ---- action embedding + conv3 weight gradient (side) -------------------------------------
+  DRL_TRY(fork_to_side(st, 4));
+  s = side;
   KERNEL("emb_bwd",
          emb_backward(s, bw.du, in.pa, act.e1, act.table, P + pl.emb2_w, bw.dpre2, bw.dpre1, G + pl.emb1_w,
                       G + pl.emb1_b, G + pl.emb2_w, G + pl.emb2_b, bw.wg_part, Mb, B, T, A), 4);
@@ -261,6 +296,7 @@ int net_backward(cudaStream_t s, const ParamLayout& pl, const float* P, float* G
     GEMM("conv3_wgrad", CfgBig, U64, al, bl, ep, 576, 64, Mb * 49, sp.splits, sp.kchunk, sp.kchunk);
     KERNEL("conv3_wgrad_reduce", splitk_reduce(s, bw.wg_part, slab, sp.splits, G + pl.conv3_w, slab), 1);
   }
+  s = st.main;
   {
     Conv3DA al{bw.da3};
     Conv3DB bl{P + pl.conv3_w};
@@ -268,6 +304,8 @@ int net_backward(cudaStream_t s, const ParamLayout& pl, const float* P, float* G
     GEMM("conv3_dgrad", CfgBig, U64, al, bl, ep, Mb * 81, 64, 576, 1, 576, 0);
   }
   // ---- conv2 -------------------------------------------------------------------------------
+  DRL_TRY(fork_to_side(st, 5));
+  s = side;
   {
     const SplitPlan sp = plan_conv2_wgrad(Mb, mode);
     const size_t slab = 513 * 64;
@@ -277,6 +315,7 @@ int net_backward(cudaStream_t s, const ParamLayout& pl, const float* P, float* G
     GEMM("conv2_wgrad", CfgBig, U64, al, bl, ep, 512, 64, Mb * 81, sp.splits, sp.kchunk, sp.kchunk);
     KERNEL("conv2_wgrad_reduce", splitk_reduce(s, bw.wg_part, slab, sp.splits, G + pl.conv2_w, slab), 1);
   }
+  s = st.main;
   {
     Conv2DA al{bw.da2};
     Conv2DB bl{P + pl.conv2_w};
@@ -289,10 +328,11 @@ int net_backward(cudaStream_t s, const ParamLayout& pl, const float* P, float* G
     const size_t slab = 257 * 32;
     Conv1WA al{in.frames, map};
     PlainB bl{bw.da1, 32, 0};
-    EpRaw<true> ep{bw.wg_part, 32, slab, 1.0f / 255.0f, 256, 32};
+    EpRaw<true> ep{bw.wg_part2, 32, slab, 1.0f / 255.0f, 256, 32};   // own partial buffer: runs beside the side stream
     GEMM("conv1_wgrad", CfgWg1, U32, al, bl, ep, 256, 32, Mb * 400, sp.splits, sp.kchunk, sp.kchunk);
-    KERNEL("conv1_wgrad_reduce", splitk_reduce(s, bw.wg_part, slab, sp.splits, G + pl.conv1_w, slab), 1);
+    KERNEL("conv1_wgrad_reduce", splitk_reduce(s, bw.wg_part2, slab, sp.splits, G + pl.conv1_w, slab), 1);
   }
+  DRL_TRY(join_from_side(st, 6));
   g_bwd_launches = n;
   return DRL_OK;
 }

@@ -52,8 +52,10 @@ struct drl_learner {
   drl_learner_config cfg{};
   int B = 0, T = 0, A = 0, M = 0, Mb = 0, mode = 1;
   ParamLayout pl{};
-  cudaStream_t compute = nullptr, copy = nullptr;
+  cudaStream_t compute = nullptr, copy = nullptr, side = nullptr;
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done = nullptr;
+  cudaEvent_t fj[8] = {};    // fork/join events between the compute and the side stream
+  bool par = true;           // run off-critical-path kernels on the side stream
   float* params = nullptr;
   float* ms = nullptr;
   float* bucket = nullptr;   // [padded_total grads | 4 loss sums]
@@ -118,8 +120,17 @@ int download_flat(drl_learner* h, const float* dev_padded, float* host_packed) {
   return DRL_OK;
 }
 
+Streams streams_of(const drl_learner* h) {
+  Streams st;
+  st.main = h->compute;
+  st.side = h->side;
+  for (int i = 0; i < 8; ++i) st.ev[i] = h->fj[i];
+  st.par = h->par;
+  return st;
+}
+
 int enqueue_forward(drl_learner* h, const Inputs& in, int B, int T) {
-  return net_forward(h->compute, h->pl, h->params, in, h->act, B, T, h->mode);
+  return net_forward(streams_of(h), h->pl, h->params, in, h->act, B, T, h->mode);
 }
 
 int enqueue_forward_backward(drl_learner* h, int slot) {
@@ -129,7 +140,7 @@ int enqueue_forward_backward(drl_learner* h, int slot) {
   prof_mark(h->compute, "vtrace_losses");
   DRL_TRY(vtrace_losses(h->compute, vc, h->act.policy, h->act.value, in, h->vt, h->bwd.dlogits, h->bwd.dv, h->B,
                         h->T, h->A));
-  DRL_TRY(net_backward(h->compute, h->pl, h->params, h->bucket, in, h->act, h->bwd, h->B, h->T, h->mode));
+  DRL_TRY(net_backward(streams_of(h), h->pl, h->params, h->bucket, in, h->act, h->bwd, h->B, h->T, h->mode));
   return DRL_OK;
 }
 
@@ -233,6 +244,8 @@ int drl_learner_create(const drl_learner_config* cfg, drl_learner** out) {
     DRL_TRY(set_device(h));
     DRL_CUDA_CHECK(cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
     DRL_CUDA_CHECK(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
+    DRL_CUDA_CHECK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; ++i) DRL_CUDA_CHECK(cudaEventCreateWithFlags(&h->fj[i], cudaEventDisableTiming));
     DRL_CUDA_CHECK(cudaEventCreate(&h->ev_start));
     DRL_CUDA_CHECK(cudaEventCreate(&h->ev_stop));
     DRL_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
@@ -275,6 +288,7 @@ int drl_learner_create(const drl_learner_config* cfg, drl_learner** out) {
     DRL_TRY(dev_alloc(h, &b.da1, Mb * 400 * 32));
     b.wg_part_floats = wgrad_partial_floats(h->B, h->T);
     DRL_TRY(dev_alloc(h, &b.wg_part, b.wg_part_floats));
+    DRL_TRY(dev_alloc(h, &b.wg_part2, b.wg_part_floats));
     VtraceOut& v = h->vt;
     const size_t nt = (size_t)h->B * (h->T - 2);
     DRL_TRY(dev_alloc(h, &v.vs, nt));
@@ -352,6 +366,8 @@ int drl_learner_destroy(drl_learner* h) {
   if (h->ev_start) cudaEventDestroy(h->ev_start);
   if (h->ev_stop) cudaEventDestroy(h->ev_stop);
   if (h->ev_done) cudaEventDestroy(h->ev_done);
+  for (int i = 0; i < 8; ++i) if (h->fj[i]) cudaEventDestroy(h->fj[i]);
+  if (h->side) cudaStreamDestroy(h->side);
   if (h->compute) cudaStreamDestroy(h->compute);
   if (h->copy) cudaStreamDestroy(h->copy);
   cudaGetLastError();
@@ -598,8 +614,11 @@ int drl_learner_profile_step(drl_learner* h, int32_t slot, char* names, int64_t 
   g_prof.on = true;
   g_prof.ev.clear();
   g_prof.names.clear();
+  const bool par_saved = h->par;
+  h->par = false;                       // serial: the event-to-event times are then per kernel
   int rc = enqueue_forward_backward(h, slot);
   if (rc == DRL_OK) rc = enqueue_apply(h);
+  h->par = par_saved;
   g_prof.on = false;
   cudaError_t e = cudaStreamSynchronize(h->compute);
   int n = 0;
