@@ -21,8 +21,9 @@ static int run_one(int core, int bn, cudaStream_t s, const AL& al, const BL& bl,
   switch (bn) {
     case 32: return launch_gemm_umma<UmmaCfg<32, 2, 2>>(s, al, bl, ep, M, N, K, nz, kchunk, kchunk);
     case 64: return launch_gemm_umma<UmmaCfg<64, 2, 2>>(s, al, bl, ep, M, N, K, nz, kchunk, kchunk);
-    case 128: return launch_gemm_umma<UmmaCfg<128, 3, 1>>(s, al, bl, ep, M, N, K, nz, kchunk, kchunk);
-    default: set_error("debug_gemm: bn must be 32, 64 or 128"); return DRL_ERR_INVALID;
+    case 128: return launch_gemm_umma<UmmaCfg<128, 3, 1, 8>>(s, al, bl, ep, M, N, K, nz, kchunk, kchunk);
+    case 256: return launch_gemm_umma<UmmaCfg<256, 2, 1, 8>>(s, al, bl, ep, M, N, K, nz, kchunk, kchunk);
+    default: set_error("debug_gemm: bn must be 32, 64, 128 or 256"); return DRL_ERR_INVALID;
   }
 }
 

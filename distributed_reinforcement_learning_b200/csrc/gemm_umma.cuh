@@ -8,13 +8,13 @@
 // concepts as gemm_simt.cuh, so every layer of layers.cu can run on either core.
 //
 // Structure (one 128 x BN output tile per CTA, 160 threads, 1 CTA per SM):
-//   warps 0-3 : PRODUCERS, then EPILOGUE.  Each thread gathers float4 groups of A and B through the
+//   warps 0..PW-1 (PW = 4 or 8): PRODUCERS, then EPILOGUE.  Each thread gathers float4 groups of A and B through the
 //               loader functors (im2col, concat, transposes happen here -- which is why TMA cannot
 //               stage these operands), splits them into hi/lo and writes both into the stage's
 //               shared-memory operand tiles in the canonical 128-byte-swizzled UMMA layout
 //               (K-major for kContigK loaders, MN-major otherwise), then fence.proxy.async and
 //               mbarrier-arrive on full[stage].
-//   warp 4    : TMEM allocation + MMA ISSUER: waits full[stage], one lane issues 3 x (BK/8)
+//   warp PW   : TMEM allocation + MMA ISSUER: waits full[stage], one lane issues 3 x (BK/8)
 //               tcgen05.mma (M=128, N=BN, K=8) from shared-memory descriptors, then tcgen05.commit ->
 //               empty[stage]; after the last K tile tcgen05.commit -> acc_full.
 //   epilogue  : warps 0-3 read their 32 TMEM lanes (tcgen05.ld 32x32b.x32) and hand rows to the
@@ -164,11 +164,15 @@ struct UmmaTile {
   __device__ static __forceinline__ int kslice_off(int j) { return KMAJOR ? j * 32 : j * 2 * SBO; }
 };
 
-template <int BN_, int STAGES_, int MINB_ = 1>
+template <int BN_, int STAGES_, int MINB_ = 1, int PW_ = 4>
 struct UmmaCfg {
   static constexpr int BM = 128, BN = BN_, BK = 32, STAGES = STAGES_, MINB = MINB_;
-  static constexpr int NPROD = 128;     // producer / epilogue threads (warps 0-3)
-  static constexpr int NT = 160;        // + MMA warp
+  static constexpr int PW = PW_;            // producer / epilogue warps (4 or 8), warps 0..PW-1
+  static constexpr int NPROD = PW * 32;
+  static constexpr int NT = NPROD + 32;     // + the MMA warp (warp PW)
+  static constexpr int EPI_COLS = BN / (PW / 4);   // accumulator columns each producer warp drains
+  static_assert(PW == 4 || PW == 8, "4 or 8 producer warps");
+  static_assert(EPI_COLS % 32 == 0, "epilogue reads 32 columns at a time");
   static constexpr int TMEM_COLS = BN;
   static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 256, "BN must be a power of two in [32,256]");
 };
@@ -231,13 +235,13 @@ gemm_umma_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, int
     umma::mbar_init(acc_full, 1);
     umma::fence_barrier_init();
   }
-  if (warp == 4) umma::tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
+  if (warp == Cfg::PW) umma::tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
   umma::tc_fence_before();
   __syncthreads();
   umma::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp < 4) {
+  if (warp < Cfg::PW) {
     // ================= PRODUCERS =================
     // K-major operand : group g -> row g/8, chunk g%8  (8 lanes cover one 128-byte row: coalesced global
     //                   read of 128 contiguous bytes, conflict-free swizzled 16-byte stores)
@@ -343,7 +347,7 @@ gemm_umma_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, int
 #pragma unroll
       for (int i = 0; i < GB; ++i) { acc.x += csum[i].x; acc.y += csum[i].y; acc.z += csum[i].z; acc.w += csum[i].w; }
       cs_scratch[tid] = acc;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");
       if (tid < BN / 4) {
         float4 tot = zero4();
         for (int j = tid; j < NPROD; j += BN / 4) {
@@ -361,11 +365,13 @@ gemm_umma_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, int
     // ================= EPILOGUE =================
     umma::mbar_wait(acc_full, 0);
     umma::tc_fence_after();
-    const int m = m0 + warp * 32 + lane;
+    // warp w may only touch TMEM lanes 32*(w%4)..+31; with 8 warps the two warps of a lane quarter split the columns
+    const int m = m0 + (warp & 3) * 32 + lane;
+    const int cbeg = (warp >> 2) * Cfg::EPI_COLS;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = cbeg; c0 < cbeg + Cfg::EPI_COLS; c0 += 32) {
       float v[32];
-      umma::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      umma::tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, v);
       if (m < M) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
@@ -420,7 +426,7 @@ gemm_umma_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, int
     umma::tc_fence_before();
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == Cfg::PW) {
     umma::tc_fence_after();
     umma::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }

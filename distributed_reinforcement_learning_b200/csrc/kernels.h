@@ -78,11 +78,11 @@ struct VtraceOut {       // parity taps, batch-major [B, T-2]
   float* loss_sums;      // [4] pi, baseline, entropy, (pad) -- tail of the gradient bucket
 };
 
-constexpr int kLstmSplits = 4;
+constexpr int kLstmSplits = 8;   // slabs allocated for the LSTM split-K partial sums (4 or 7 are used)
 
 // math_mode 0 in drl_learner_config resolves to this (1 = FP32 FFMA, 2 = tcgen05 3xTF32)
 #ifndef DRL_DEFAULT_MATH_MODE
-#define DRL_DEFAULT_MATH_MODE 1
+#define DRL_DEFAULT_MATH_MODE 2
 #endif
 
 // Per-kernel device timing (learner.cu): when a profile run is active, prof_mark records a CUDA event

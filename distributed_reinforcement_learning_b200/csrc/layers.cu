@@ -57,7 +57,8 @@ using Conv2DE = EpConvDx<20, 20, 32, 2, 10, 10>;
 
 using U32 = UmmaCfg<32, 2, 2>;   // 40 KB / stage (24 KB when A is exact), 2 CTAs per SM
 using U64 = UmmaCfg<64, 2, 2>;   // 48 KB / stage, 2 CTAs per SM
-using U128 = UmmaCfg<128, 3, 1>; // 64 KB / stage, 1 CTA per SM
+using U128 = UmmaCfg<128, 3, 1, 8>;   // 64 KB / stage, 1 CTA per SM, 8 producer warps
+using U256 = UmmaCfg<256, 2, 1, 8>;   // 96 KB / stage, 1 CTA per SM, 8 producer warps
 
 static int g_fwd_launches = 0, g_bwd_launches = 0;
 int forward_launch_count() { return g_fwd_launches; }
@@ -142,7 +143,7 @@ int net_forward(const Streams& st, const ParamLayout& pl, const float* P, const 
                 int T, int mode) {
   const int M = B * T;
   const RowMap map{B, T};
-  int n = 0;
+  int n = 0, nsplit = 4;
   cudaStream_t s = st.main;
   const cudaStream_t side = st.par ? st.side : st.main;
   // action embedding table (:12-16): only A distinct inputs exist; depends on parameters only -> side stream
@@ -178,11 +179,13 @@ int net_forward(const Streams& st, const ParamLayout& pl, const float* P, const 
     LstmA al{act.a3, act.table, in.pa, in.h0, map};
     PlainB bl{P + pl.lstm_w, Geo::G4, 0};
     EpRaw<false> ep{act.zpart, Geo::G4, (size_t)M * Geo::G4, 1.0f, 0, Geo::G4};
-    const int kchunk = (mode == 2) ? 928 : Geo::XK / kLstmSplits;   // 29 x 32 | 57 x 16 ; 4 splits either way
-    GEMM("lstm_fwd", CfgMid, U128, al, bl, ep, M, Geo::G4, Geo::XK, kLstmSplits, kchunk, kchunk);
+    // FFMA: 4 splits of 57 x 16.  tcgen05: 128 x 256 tiles -> 5 x 4 output tiles x 7 splits of 17 x 32 = 140 CTAs (one wave)
+    nsplit = (mode == 2) ? 7 : 4;
+    const int kchunk = (mode == 2) ? 544 : Geo::XK / 4;
+    GEMM("lstm_fwd", CfgMid, U256, al, bl, ep, M, Geo::G4, Geo::XK, nsplit, kchunk, kchunk);
   }
   KERNEL("lstm_gates_fwd",
-         lstm_gates_forward(s, act.zpart, kLstmSplits, P + pl.lstm_b, in.c0, act.gates, act.c1, act.tc1, act.h1, M, B,
+         lstm_gates_forward(s, act.zpart, nsplit, P + pl.lstm_b, in.c0, act.gates, act.c1, act.tc1, act.h1, M, B,
                             T), 1);
   // heads (fully_connected, :27-30,40-41): z = 0 actor, z = 1 critic
   const size_t head_stride = (size_t)(pl.critic1_w - pl.actor1_w);
@@ -271,7 +274,7 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, float
     LstmAT al{act.a3, act.table, in.pa, in.h0, map};
     PlainB bl{bw.dz, Geo::G4, 0};
     EpRaw<true> ep{G + pl.lstm_w, Geo::G4, 0, 1.0f, Geo::XK, Geo::G4};
-    GEMM("lstm_wgrad", CfgBig, U128, al, bl, ep, Geo::XK, Geo::G4, Mb, 1, Mb, 0);
+    GEMM("lstm_wgrad", CfgBig, U256, al, bl, ep, Geo::XK, Geo::G4, Mb, 1, Mb, 0);   // 29 x 4 = 116 CTAs: one wave
   }
   s = st.main;
   {  // d[a3 | emb] = dz W[:3392]^T  (h0, c0 are fed data: no gradient, agent/impala.py:38-39)

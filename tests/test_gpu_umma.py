@@ -34,7 +34,7 @@ def _gemm(native, core, bn, a_km, b_km, M, N, K, splits, seed=0):
 
 
 @pytest.mark.parametrize("a_km,b_km", [(1, 0), (1, 1), (0, 0), (0, 1)])
-@pytest.mark.parametrize("bn", [32, 64, 128])
+@pytest.mark.parametrize("bn", [32, 64, 128, 256])
 def test_umma_gemm_operand_majors(native, a_km, b_km, bn):
     err, cs = _gemm(native, 2, bn, a_km, b_km, 256, 128, 96, 1)
     assert err < 1e-5, (a_km, b_km, bn, err)
@@ -43,7 +43,7 @@ def test_umma_gemm_operand_majors(native, a_km, b_km, bn):
 
 
 @pytest.mark.parametrize("M,N,K,splits,bn", [(128, 32, 32, 1, 32), (132, 36, 100, 1, 64), (640, 1024, 3648, 4, 128),
-                                             (3648, 1024, 576, 1, 128), (52, 64, 4096, 7, 64), (1000, 200, 68, 2, 128)])
+                                             (3648, 1024, 576, 1, 256), (640, 1024, 3648, 7, 256), (52, 64, 4096, 7, 64), (1000, 200, 68, 2, 128)])
 @pytest.mark.parametrize("a_km,b_km", [(1, 0), (0, 0), (1, 1)])
 def test_umma_gemm_shapes_and_splitk(native, M, N, K, splits, bn, a_km, b_km):
     err, cs = _gemm(native, 2, bn, a_km, b_km, M, N, K, splits, seed=M + N)
@@ -65,6 +65,12 @@ def _assert_all(errs):
 
 def test_step_small_config_tensor_core_path(native):
     _assert_all(parity.compare_step(4, T=20, math_mode=2))
+
+
+def test_step_ffma_path(native):
+    """math_mode=1 (FP32 FFMA contractions) stays covered now that the tensor-core path is the default."""
+    _assert_all(parity.compare_step(4, T=20, math_mode=1))
+    _assert_all(parity.compare_step(32, T=20, layers=False, math_mode=1))
 
 
 def test_step_reference_config_tensor_core_path(native):
