@@ -185,6 +185,13 @@ struct loader_exact : std::false_type {};
 template <class L>
 struct loader_exact<L, std::void_t<decltype(L::kExactTf32)>> : std::bool_constant<L::kExactTf32> {};
 
+// A loader may also declare `kVec16`: it then provides load_raw16()/unpack16() that fetch 16 consecutive
+// elements of the contiguous dimension with ONE 128-bit load (the uint8 frames: 4x fewer load instructions).
+template <class L, class = void>
+struct loader_vec16 : std::false_type {};
+template <class L>
+struct loader_vec16<L, std::void_t<decltype(L::kVec16)>> : std::bool_constant<L::kVec16> {};
+
 template <class Cfg, class AL, class BL>
 struct UmmaSmem {
   using TA = UmmaTile<Cfg::BM, AL::kContigK>;
@@ -206,8 +213,11 @@ gemm_umma_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, int
   using TB = typename SM::TB;
   constexpr bool AEX = SM::AEX;
   constexpr int NGA = BM * BK / 4, NGB = BN * BK / 4;       // float4 groups per stage
-  constexpr int GA = NGA / NPROD, GB = NGB / NPROD;          // per producer thread (8 and BN/16)
-  static_assert(NGA % NPROD == 0 && NGB % NPROD == 0, "groups must divide among producers");
+  constexpr bool A16 = loader_vec16<AL>::value;              // 16-element (one 128-bit load) A groups
+  constexpr int GA = (A16 ? NGA / 4 : NGA) / NPROD, GB = NGB / NPROD;   // groups per producer thread
+  static_assert((A16 ? NGA / 4 : NGA) % NPROD == 0 && NGB % NPROD == 0, "groups must divide among producers");
+  static_assert(!A16 || AEX, "16-wide raw loads are only used for exact (uint8) operands");
+  using ARaw = typename std::conditional<A16, uint4, float4>::type;
   constexpr bool kColSum = EP::kColSum && !BKc;
   constexpr int OFF_ALO = SM::A_BYTES, OFF_BHI = (AEX ? 1 : 2) * SM::A_BYTES, OFF_BLO = OFF_BHI + SM::B_BYTES;
 
@@ -253,7 +263,19 @@ gemm_umma_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, int
 #pragma unroll
     for (int i = 0; i < GA; ++i) {
       const int g = tid + i * NPROD;
-      if (AK) {
+      if (A16) {
+        if (AK) {   // group = (row, 16-k half): 32 lanes = 32 consecutive rows -> coalesced, conflict-free stores
+          const int r = g % BM, half = g / BM;
+          arow[i] = al.row(z, (m0 + r < M) ? m0 + r : -1);
+          a_k[i] = half * 16;
+          a_o[i] = r;
+        } else {    // group = (k, 16 consecutive mn): 32 lanes = the 32 k of the tile for the same 16 mn values
+          const int kk = g % BK, q16 = g / BK;
+          arow[i] = al.row(z, (m0 + q16 * 16 < M) ? m0 + q16 * 16 : -1);
+          a_k[i] = kk;
+          a_o[i] = q16 * 16;
+        }
+      } else if (AK) {
         const int r = g >> 3, kq = g & 7;
         arow[i] = al.row(z, (m0 + r < M) ? m0 + r : -1);
         a_k[i] = kq * 4;
@@ -285,12 +307,13 @@ gemm_umma_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, int
     for (int i = 0; i < GB; ++i) csum[i] = zero4();
 
     // gather tile t into registers
-    auto gload = [&](int t, float4 (&ra)[GA], float4 (&rb)[GB]) {
+    auto gload = [&](int t, ARaw (&ra)[GA], float4 (&rb)[GB]) {
       const int kb = k0 + t * BK;
 #pragma unroll
       for (int i = 0; i < GA; ++i) {
         const int k = kb + a_k[i];
-        ra[i] = (k < k1) ? al.load(arow[i], k) : zero4();
+        if constexpr (A16) ra[i] = (k < k1) ? al.load_raw16(arow[i], k) : make_uint4(0u, 0u, 0u, 0u);
+        else ra[i] = (k < k1) ? al.load(arow[i], k) : zero4();
       }
 #pragma unroll
       for (int i = 0; i < GB; ++i) {
@@ -299,14 +322,22 @@ gemm_umma_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, int
       }
     };
     // split tile t into hi/lo and publish it in its shared-memory stage
-    auto publish = [&](int t, const float4 (&ra)[GA], const float4 (&rb)[GB]) {
+    auto publish = [&](int t, const ARaw (&ra)[GA], const float4 (&rb)[GB]) {
       const int s = t % STAGES;
       const uint32_t ph = (t / STAGES) & 1;
       umma::mbar_wait(&empty[s], ph ^ 1);
       uint8_t* st = smem + s * SM::STAGE_BYTES;
 #pragma unroll
       for (int i = 0; i < GA; ++i) {
-        if (AEX) {
+        if constexpr (A16) {
+          float4 f[4];
+          AL::unpack16(ra[i], f);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int off = AK ? TA::chunk_off(a_o[i], a_k[i] + 4 * j) : TA::chunk_off(a_o[i] + 4 * j, a_k[i]);
+            *reinterpret_cast<float4*>(st + off) = f[j];
+          }
+        } else if constexpr (AEX) {
           *reinterpret_cast<float4*>(st + a_o[i]) = ra[i];
         } else {
           float4 h, l;
@@ -328,7 +359,8 @@ gemm_umma_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, int
     };
 
     // register double buffering: the gathers of tile t+1 are in flight while tile t is split and stored
-    float4 ra0[GA], rb0[GB], ra1[GA], rb1[GB];
+    ARaw ra0[GA], ra1[GA];
+    float4 rb0[GB], rb1[GB];
     if (ntiles > 0) gload(0, ra0, rb0);
 #pragma unroll 1
     for (int t = 0; t < ntiles; t += 2) {

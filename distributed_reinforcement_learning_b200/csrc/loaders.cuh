@@ -12,6 +12,13 @@ namespace drl {
 __device__ __forceinline__ float4 u8x4_to_f4(uchar4 u) {
   return make_float4((float)u.x, (float)u.y, (float)u.z, (float)u.w);
 }
+__device__ __forceinline__ float4 u32_bytes_to_f4(uint32_t w) {
+  return make_float4((float)(w & 0xffu), (float)((w >> 8) & 0xffu), (float)((w >> 16) & 0xffu), (float)(w >> 24));
+}
+// 16 frame bytes (one 128-bit load) -> 16 floats
+__device__ __forceinline__ void unpack_u8x16(const uint4& u, float4 (&f)[4]) {
+  f[0] = u32_bytes_to_f4(u.x); f[1] = u32_bytes_to_f4(u.y); f[2] = u32_bytes_to_f4(u.z); f[3] = u32_bytes_to_f4(u.w);
+}
 
 // time-major row index -> batch-major source index
 struct RowMap {
@@ -55,6 +62,15 @@ struct ConvFwdA {
       return __ldg(reinterpret_cast<const float4*>(p));
     }
   }
+  // uint8 operands: 16 consecutive k (k multiple of 16) are 16 contiguous, 16-byte aligned frame bytes
+  static constexpr bool kVec16 = (sizeof(T) == 1) && ((KW * C) % 16 == 0);
+  __device__ __forceinline__ uint4 load_raw16(const Row& r, int k) const {
+    if (r.base == nullptr) return make_uint4(0u, 0u, 0u, 0u);
+    const int ky = k / (KW * C);
+    const int rr = k - ky * (KW * C);
+    return __ldg(reinterpret_cast<const uint4*>(r.base + ky * (IW * C) + rr));
+  }
+  __device__ static __forceinline__ void unpack16(const uint4& u, float4 (&f)[4]) { unpack_u8x16(u, f); }
 };
 
 // Weight-gradient A operand: C[i, co] = sum_r X(i, r) dY(r, co); i = (ky,kx,ci) is the contiguous
@@ -86,6 +102,17 @@ struct ConvWgradA {
       return __ldg(reinterpret_cast<const float4*>(ptr));
     }
   }
+  // uint8 operands: 16 consecutive features i (i multiple of 16) of one output pixel are 16 contiguous bytes
+  static constexpr bool kVec16 = (sizeof(T) == 1) && ((KW * C) % 16 == 0) && ((S * C) % 16 == 0);
+  __device__ __forceinline__ uint4 load_raw16(const Row& r, int rr) const {
+    if (r.off < 0) return make_uint4(0u, 0u, 0u, 0u);
+    const int img = rr / (OH * OW);
+    const int p = rr - img * (OH * OW);
+    const int oy = p / OW, ox = p - oy * OW;
+    const int simg = REMAP ? map.src(img) : img;
+    return __ldg(reinterpret_cast<const uint4*>(x + (size_t)simg * (IH * IW * C) + ((oy * S) * IW + ox * S) * C + r.off));
+  }
+  __device__ static __forceinline__ void unpack16(const uint4& u, float4 (&f)[4]) { unpack_u8x16(u, f); }
 };
 
 // Data-gradient A operand (gather form): rows are input pixels of parity class z = (py,px)
