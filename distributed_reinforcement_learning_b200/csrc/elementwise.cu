@@ -285,6 +285,60 @@ int emb_backward(cudaStream_t s, const float* du, const int32_t* pa, const float
 }
 
 // ------------------------------------------------------------------------------------------
+// col2im + ReLU mask: second half of the convolution data gradient in its "dCol" form
+//   dCol[(img,oy,ox), (ky,kx,ci)] = sum_co dY[img,oy,ox,co] W[ky,kx,ci,co]         (one plain GEMM, K = CO)
+//   dX[img,y,x,ci] = relu'(act) * sum_{ky,kx : (y-ky)%S == 0, (x-kx)%S == 0, oy,ox in range} dCol[(img,oy,ox),(ky,kx,ci)]
+// One thread per (pixel, 4 channels): <= (KH/S)*(KW/S) float4 reads, deterministic (a gather, no atomics).
+// ------------------------------------------------------------------------------------------
+template <int IH, int IW, int CI, int OH, int OW, int KH, int KW, int S>
+__global__ void __launch_bounds__(256) col2im_relu_kernel(const float* __restrict__ dcol,
+                                                           const float* __restrict__ act, float* __restrict__ dx,
+                                                           int nimg) {
+  constexpr int C4 = CI / 4, NCOL = KH * KW * CI;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)nimg * IH * IW * C4;
+  if (idx >= total) return;
+  const int c4 = (int)(idx % C4);
+  const long long pix = idx / C4;
+  const int x = (int)(pix % IW);
+  const int y = (int)((pix / IW) % IH);
+  const int img = (int)(pix / (IW * IH));
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int jy = 0; jy < KH / S; ++jy) {
+    const int ky = (y % S) + jy * S;
+    const int oy = (y - ky) / S;
+    if (oy < 0 || oy >= OH) continue;
+#pragma unroll
+    for (int jx = 0; jx < KW / S; ++jx) {
+      const int kx = (x % S) + jx * S;
+      const int ox = (x - kx) / S;
+      if (ox < 0 || ox >= OW) continue;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(
+          dcol + ((size_t)(img * OH + oy) * OW + ox) * NCOL + (ky * KW + kx) * CI + c4 * 4));
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  const size_t o = (size_t)pix * CI + c4 * 4;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(act + o));
+  *reinterpret_cast<float4*>(dx + o) = make_float4(a.x > 0.f ? acc.x : 0.f, a.y > 0.f ? acc.y : 0.f,
+                                                   a.z > 0.f ? acc.z : 0.f, a.w > 0.f ? acc.w : 0.f);
+}
+
+int col2im_conv3(cudaStream_t s, const float* dcol, const float* a2, float* da2, int nimg) {
+  const long long total = (long long)nimg * 9 * 9 * 16;
+  col2im_relu_kernel<9, 9, 64, 7, 7, 3, 3, 1><<<(unsigned)cdiv64(total, 256), 256, 0, s>>>(dcol, a2, da2, nimg);
+  DRL_CHECK_LAUNCH();
+  return DRL_OK;
+}
+int col2im_conv2(cudaStream_t s, const float* dcol, const float* a1, float* da1, int nimg) {
+  const long long total = (long long)nimg * 20 * 20 * 8;
+  col2im_relu_kernel<20, 20, 32, 9, 9, 4, 4, 2><<<(unsigned)cdiv64(total, 256), 256, 0, s>>>(dcol, a1, da1, nimg);
+  DRL_CHECK_LAUNCH();
+  return DRL_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // out[j] = sum_z part[z*slab + j]   (deterministic split-K reduction)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, size_t slab, int nsplit,

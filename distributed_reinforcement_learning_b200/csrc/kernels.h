@@ -68,6 +68,7 @@ struct Bwd {             // backward workspace, Mb = B*(T-2) rows
   float* da1;            // [Mb,20,20,32]
   float* wg_part;        // split-K partial slabs for the conv3/conv2 weight gradients (side stream) + emb scratch
   float* wg_part2;       // split-K partial slabs for the conv1 weight gradient (main stream)
+  float* dcol;           // [Mb*81, 512] (conv2) / [Mb*49, 576] (conv3): per-output-pixel tap gradients before col2im
   size_t wg_part_floats;
 };
 
@@ -123,6 +124,9 @@ int emb_backward(cudaStream_t s, const float* du, const int32_t* pa, const float
                  const float* w2, float* dpre2, float* dpre1, float* g_w1, float* g_b1, float* g_w2, float* g_b2,
                  float* scratch, int Mb, int B, int T, int A);
 int splitk_reduce(cudaStream_t s, const float* part, size_t slab, int nsplit, float* out, size_t n);
+// second half of the "dCol" form of the conv data gradients (gather of <= 9 / 4 taps + ReLU mask)
+int col2im_conv3(cudaStream_t s, const float* dcol, const float* a2, float* da2, int nimg);
+int col2im_conv2(cudaStream_t s, const float* dcol, const float* a1, float* da1, int nimg);
 
 // ---- vtrace.cu ----------------------------------------------------------------------------
 struct VtraceCfg {

@@ -300,11 +300,21 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, float
     KERNEL("conv3_wgrad_reduce", splitk_reduce(s, bw.wg_part, slab, sp.splits, G + pl.conv3_w, slab), 1);
   }
   s = st.main;
-  {
+  if (mode == 2) {
+    // "dCol" form: one plain GEMM with K = 64 output channels (instead of gathering every dY value 9 times
+    // through the producers), then a gather of <= 9 taps per input pixel with the ReLU mask.
+    PlainA al{bw.da3, 64, 0};
+    PlainBT bl{P + pl.conv3_w, 64, 0};               // B(k = co, n = (ky,kx,ci)) = W[n*64 + co]
+    EpRaw<false> ep{bw.dcol, 576, 0, 1.0f, 0, 576};
+    prof_mark(s, "conv3_dgrad");
+    DRL_TRY((launch_gemm_umma<U256>(s, al, bl, ep, Mb * 49, 576, 64, 1, 64, 0)));
+    DRL_TRY(col2im_conv3(s, bw.dcol, act.a2, bw.da2, Mb));
+    n += 2;
+  } else {
     Conv3DA al{bw.da3};
     Conv3DB bl{P + pl.conv3_w};
     Conv3DE ep{bw.da2, act.a2};
-    GEMM("conv3_dgrad", CfgBig, U64, al, bl, ep, Mb * 81, 64, 576, 1, 576, 0);
+    GEMM_FFMA("conv3_dgrad", CfgBig, al, bl, ep, Mb * 81, 64, 576, 1, 576, 0);
   }
   // ---- conv2 -------------------------------------------------------------------------------
   DRL_TRY(fork_to_side(st, 5));
@@ -319,11 +329,19 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, float
     KERNEL("conv2_wgrad_reduce", splitk_reduce(s, bw.wg_part, slab, sp.splits, G + pl.conv2_w, slab), 1);
   }
   s = st.main;
-  {
+  if (mode == 2) {
+    PlainA al{bw.da2, 64, 0};
+    PlainBT bl{P + pl.conv2_w, 64, 0};               // B(k = co, n = (ky,kx,ci)) = W[n*64 + co]
+    EpRaw<false> ep{bw.dcol, 512, 0, 1.0f, 0, 512};
+    prof_mark(s, "conv2_dgrad");
+    DRL_TRY((launch_gemm_umma<U256>(s, al, bl, ep, Mb * 81, 512, 64, 1, 64, 0)));
+    DRL_TRY(col2im_conv2(s, bw.dcol, act.a1, bw.da1, Mb));
+    n += 2;
+  } else {
     Conv2DA al{bw.da2};
     Conv2DB bl{P + pl.conv2_w};
     Conv2DE ep{bw.da1, act.a1};
-    GEMM("conv2_dgrad", CfgN32, U32, al, bl, ep, Mb * 100, 32, 256, 4, 256, 0);
+    GEMM_FFMA("conv2_dgrad", CfgN32, al, bl, ep, Mb * 100, 32, 256, 4, 256, 0);
   }
   // ---- conv1 (input is data: weight gradient only) -----------------------------------------
   {

@@ -289,6 +289,7 @@ int drl_learner_create(const drl_learner_config* cfg, drl_learner** out) {
     b.wg_part_floats = wgrad_partial_floats(h->B, h->T);
     DRL_TRY(dev_alloc(h, &b.wg_part, b.wg_part_floats));
     DRL_TRY(dev_alloc(h, &b.wg_part2, b.wg_part_floats));
+    DRL_TRY(dev_alloc(h, &b.dcol, Mb * 81 * 512));
     VtraceOut& v = h->vt;
     const size_t nt = (size_t)h->B * (h->T - 2);
     DRL_TRY(dev_alloc(h, &v.vs, nt));

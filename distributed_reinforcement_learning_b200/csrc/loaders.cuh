@@ -331,6 +331,14 @@ struct EpReluMask {
     const size_t o = (size_t)m * ldc + n;
     float* pc = c + z * sz_c + o;
     const float* pa = act + z * sz_act + o;
+    if constexpr (V == 4) {
+      if ((ldc & 3) == 0) {          // n is a multiple of 4 here: 16-byte aligned
+        const float4 a = __ldg(reinterpret_cast<const float4*>(pa));
+        *reinterpret_cast<float4*>(pc) = make_float4(a.x > 0.f ? v[0] : 0.f, a.y > 0.f ? v[1] : 0.f,
+                                                     a.z > 0.f ? v[2] : 0.f, a.w > 0.f ? v[3] : 0.f);
+        return;
+      }
+    }
 #pragma unroll
     for (int j = 0; j < V; ++j) pc[j] = (__ldg(pa + j) > 0.f) ? v[j] : 0.f;
   }
@@ -342,6 +350,17 @@ struct EpLstmDx {
   float* da3; const float* a3; float* du;
   template <int V>
   __device__ __forceinline__ void store(int, int m, int n, const float (&v)[V]) const {
+    if constexpr (V == 4) {          // FLAT and EMB are multiples of 4: a 4-group never straddles the boundary
+      if (n < Geo::FLAT) {
+        const size_t o = (size_t)m * Geo::FLAT + n;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(a3 + o));
+        *reinterpret_cast<float4*>(da3 + o) = make_float4(a.x > 0.f ? v[0] : 0.f, a.y > 0.f ? v[1] : 0.f,
+                                                          a.z > 0.f ? v[2] : 0.f, a.w > 0.f ? v[3] : 0.f);
+      } else {
+        *reinterpret_cast<float4*>(du + (size_t)m * Geo::EMB + (n - Geo::FLAT)) = make_float4(v[0], v[1], v[2], v[3]);
+      }
+      return;
+    }
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       const int nn = n + j;
@@ -367,8 +386,14 @@ struct EpConvDx {
     const int yy = p / RW, xx = p - yy * RW;
     const int py = z / S, px = z - py * S;
     const size_t o = ((size_t)(img * IH + yy * S + py) * IW + (xx * S + px)) * CI + n;
+    if constexpr (V == 4) {          // CI is a multiple of 4 and n a multiple of 4: 16-byte aligned
+      const float4 a = __ldg(reinterpret_cast<const float4*>(act + o));
+      *reinterpret_cast<float4*>(dx + o) = make_float4(a.x > 0.f ? v[0] : 0.f, a.y > 0.f ? v[1] : 0.f,
+                                                       a.z > 0.f ? v[2] : 0.f, a.w > 0.f ? v[3] : 0.f);
+    } else {
 #pragma unroll
-    for (int j = 0; j < V; ++j) dx[o + j] = (__ldg(act + o + j) > 0.f) ? v[j] : 0.f;
+      for (int j = 0; j < V; ++j) dx[o + j] = (__ldg(act + o + j) > 0.f) ? v[j] : 0.f;
+    }
   }
   __device__ __forceinline__ void store_colsum(int, int, float) const {}
 };
