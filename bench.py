@@ -135,6 +135,13 @@ def kernel_flops(name, M, Mb):
     return tbl.get(name)
 
 
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) per launch at B=32, T=20 from the ncu --set full
+# capture summarised in profiles/r01_ncu_umma_full.md (tcgen05 path; conv*_dgrad = the dCol GEMM part only).
+NCU_TRAFFIC_B32 = {"lstm_fwd": 23.69e6, "lstm_wgrad": 10.26e6, "lstm_dgrad": 23.51e6, "conv1_fwd": 18.14e6,
+                   "conv2_fwd": 32.94e6, "conv3_fwd": 13.46e6, "conv1_wgrad": 45.97e6, "conv2_wgrad": 41.65e6,
+                   "conv3_wgrad": 19.21e6, "conv2_dgrad": 54.69e6, "conv3_dgrad": 20.49e6}
+
+
 def step_flops(B):
     M, Mb = B * T, B * (T - 2)
     return 2.0 * 11810048 * M + 2.0 * 2.0 * 11810048 * Mb       # SURVEY.md App. B (upper bound incl. conv1 dgrad)
@@ -310,7 +317,10 @@ def run_ours(args):
             ach = fl / (kms * 1e-3) / 1e12
             line_extra["roofline"] = {
                 "kernel": name, "bound": "tensor", "achieved": ach, "peak": peaks["tf_sus"], "unit": "TFLOP/s",
-                "frac": ach / peaks["tf_sus"], "traffic": None, "peak_source": peaks["src"] + " bf16 sustained",
+                "frac": ach / peaks["tf_sus"],
+                "traffic": NCU_TRAFFIC_B32.get(name) if args.math_mode == 2 else None,
+                "traffic_source": "profiles/r01_ncu_umma_full.md (ncu --set full, per launch)",
+                "peak_source": peaks["src"] + " bf16 sustained",
                 "math_mode": MATH_MODES[args.math_mode] + "; achieved = algorithmic 2MNK flops (counted once, "
                              "not x3) / CUDA-event time",
                 "kernel_ms": kms, "share_of_step": kms / tot}

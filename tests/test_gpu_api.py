@@ -98,9 +98,16 @@ def test_learner_loop_of_train_impala_runs_unchanged(native):
     # graph attributes double as parity taps (agent/impala.py:68-96)
     assert learner.vs.shape == (4, 18) and learner.pg_advantage.shape == (4, 18)
     assert learner.num_env_frames == 3
+    # Parameters after three updates.  This oracle run is NOT evaluated at the GPU's ReLU activation pattern
+    # (tests/parity.py explains the kink effect: a single borderline ReLU flips ~1e-3 of an image's conv
+    # gradient), so the accumulated update is compared at 1e-2 of its own size here; the 1e-4 bar is enforced
+    # by the pattern-matched harness in test_gpu_learner.py / test_gpu_umma.py.
     got = it.unflatten_params(learner._engine.get_params(), torch.float64)
     for n in L.params:
-        assert parity.rel_err(got[n].numpy(), L.params[n].detach().numpy()) < parity.TOL, n
+        p0 = params[n].double().numpy()
+        upd = L.params[n].detach().numpy() - p0
+        err = np.max(np.abs(got[n].numpy() - L.params[n].detach().numpy()))
+        assert err <= 1e-2 * np.max(np.abs(upd)) + 8 * np.finfo(np.float32).eps * np.max(np.abs(p0)), (n, err)
     # zero-copy fast path: the pinned views go straight to train (no np.stack)
     queue.append_to_queue(0, batch["state"][0], None, batch["reward"][0], batch["done"][0],
                           batch["behavior_policy"][0], batch["action"][0], batch["previous_action"][0],
