@@ -8,6 +8,7 @@
 //    affine map composition, evaluated as a warp-shuffle suffix scan (5 shuffle rounds).
 //  * vtrace_from_softmax_kernel / vtrace_fiw_kernel: the stand-alone functions with the reference's
 //    signatures and layouts ([B,T,A] batch-major and [T,B] time-major).
+#include <algorithm>
 #include <vector>
 
 #include "kernels.h"
@@ -249,6 +250,91 @@ __global__ void __launch_bounds__(kFsWarps * 32) vtrace_from_softmax_kernel(
   }
 }
 
+// Fast path of from_softmax for the learner's shape class (T <= 32, 16-byte aligned [T,A] blocks): persistent
+// warps, each looping over trajectories with a 2-stage cp.async pipeline -- the 16-byte global->shared copies of
+// trajectory b+stride are in flight (no registers, L1 bypass) while trajectory b is scanned, and the five
+// per-step scalars of the next trajectory are prefetched into registers.
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src)
+               : "memory");
+}
+__global__ void __launch_bounds__(kFsWarps * 32) vtrace_from_softmax_pipe_kernel(
+    const float* __restrict__ mu, const float* __restrict__ pi, const int32_t* __restrict__ actions,
+    const float* __restrict__ discounts, const float* __restrict__ rewards, const float* __restrict__ values,
+    const float* __restrict__ next_values, int B, int T, int A, float clip, float* __restrict__ vs,
+    float* __restrict__ clipped) {
+  extern __shared__ __align__(16) float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int TA = T * A;                               // multiple of 4 (checked by the launcher)
+  float* wbase = sm + (size_t)warp * 4 * TA;          // [stage][pi|mu][TA]
+  const int nwarps = gridDim.x * kFsWarps;
+  int b = blockIdx.x * kFsWarps + warp;
+  if (b >= B) return;
+
+  auto issue = [&](int bb, int stage) {
+    float* s_pi = wbase + stage * 2 * TA;
+    float* s_mu = s_pi + TA;
+    const float* gpi = pi + (size_t)bb * TA;
+    const float* gmu = mu + (size_t)bb * TA;
+    for (int i = lane; i < TA / 4; i += 32) {
+      cp_async16(s_pi + 4 * i, gpi + 4 * i);
+      cp_async16(s_mu + 4 * i, gmu + 4 * i);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  struct Scal { int act; float g, r, v, vn; };
+  auto scalars = [&](int bb) {
+    Scal s{0, 0.f, 0.f, 0.f, 0.f};
+    if (lane < T) {
+      const size_t o = (size_t)bb * T + lane;
+      s.act = __ldg(actions + o);
+      s.g = __ldg(discounts + o);
+      s.r = __ldg(rewards + o);
+      s.v = __ldg(values + o);
+      s.vn = (lane + 1 < T) ? __ldg(values + o + 1) : __ldg(next_values + (size_t)bb * T + T - 1);
+    }
+    return s;
+  };
+
+  issue(b, 0);
+  Scal cur = scalars(b);
+  int stage = 0;
+  for (; b < B; b += nwarps) {
+    const int nb = b + nwarps;
+    Scal nxt{0, 0.f, 0.f, 0.f, 0.f};
+    if (nb < B) {
+      issue(nb, stage ^ 1);
+      nxt = scalars(nb);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
+    const float* s_pi = wbase + stage * 2 * TA;
+    const float* s_mu = s_pi + TA;
+    float a = 1.f, d = 0.f, rb = 0.f;
+    if (lane < T) {
+      float pa = 0.f, ma = 0.f;
+      if (cur.act >= 0 && cur.act < A) { pa = s_pi[lane * A + cur.act]; ma = s_mu[lane * A + cur.act]; }
+      const float rho = expf(logf(pa) - logf(ma));
+      rb = (clip >= 0.f) ? fminf(clip, rho) : rho;
+      const float c = fminf(1.0f, rho);
+      d = rb * (cur.r + cur.g * cur.vn - cur.v);
+      a = cur.g * c;
+    }
+    warp_affine_suffix_scan(a, d, lane);
+    if (lane < T) {
+      const size_t o = (size_t)b * T + lane;
+      vs[o] = d + cur.v;
+      clipped[o] = rb;
+    }
+    cur = nxt;
+    stage ^= 1;
+    __syncwarp();      // everyone is done reading this stage before the next issue() overwrites it
+  }
+}
+
 static int launch_fiw(cudaStream_t s, const float* lr, const float* g, const float* r, const float* v,
                       const float* boot, int T, int B, float clip, float* vs, float* cl) {
   if (T < 1 || B < 1) { set_error("vtrace: T and B must be positive"); return DRL_ERR_INVALID; }
@@ -261,6 +347,18 @@ static int launch_fs(cudaStream_t s, const float* mu, const float* pi, const int
                      const float* r, const float* v, const float* nv, int B, int T, int A, float clip, float* vs,
                      float* cl) {
   if (T < 1 || B < 1 || A < 1) { set_error("vtrace: B, T, A must be positive"); return DRL_ERR_INVALID; }
+  // learner-shaped fast path: persistent warps with a cp.async pipeline
+  const size_t smem_pipe = (size_t)kFsWarps * 4 * T * A * sizeof(float);
+  if (T <= 32 && ((T * A) & 3) == 0 && ((((size_t)mu | (size_t)pi)) & 15) == 0 && smem_pipe <= 48 * 1024) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(12, (200 * 1024) / std::max<size_t>(smem_pipe, 1)));
+    const int grid = std::min(cdiv(B, kFsWarps), sms * per_sm);
+    vtrace_from_softmax_pipe_kernel<<<grid, kFsWarps * 32, smem_pipe, s>>>(mu, pi, a, g, r, v, nv, B, T, A, clip, vs, cl);
+    DRL_CHECK_LAUNCH();
+    return DRL_OK;
+  }
   const size_t smem = (size_t)kFsWarps * 2 * 32 * A * sizeof(float);
   if (smem > 200 * 1024) { set_error("vtrace: action_size %d too large", A); return DRL_ERR_INVALID; }
   static size_t smem_set = 0;
