@@ -35,7 +35,8 @@ if ROOT not in sys.path:
 T, A, L, B_PER_GPU = 20, 18, 256, 32
 METRIC = "learner env-frames/sec (T=20,B=32/GPU,84x84x4)"
 MATH_MODES = {1: "FP32 FFMA (CUDA cores)",
-              2: "tcgen05 kind::tf32, 3xTF32 split (A_lo*B_hi + A_hi*B_lo + A_hi*B_hi), fp32 TMEM accumulate"}
+              2: "tcgen05 kind::tf32, 3xTF32 split (A_lo*B_hi + A_hi*B_lo + A_hi*B_hi), fp32 TMEM accumulate",
+              3: "tcgen05 kind::tf32 3xTF32, persistent warp-specialised kernels (dedicated epilogue warps)"}
 
 
 def synth_batch(B, seed):
@@ -70,14 +71,30 @@ def measured_peaks():
 
 # ---- clocks sampling (B200_PROFILING.md) -------------------------------------------------------
 class ClockSampler:
+    """SM clock / throttle reasons sampled DURING the timed region.  The timed region of the default run is
+    only tens of milliseconds, shorter than one `nvidia-smi -lms` period, so NVML is polled directly from a
+    thread every ~2 ms (same counters as the recipe's nvidia-smi query); nvidia-smi is the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.nvml, self.samples, self.stop_flag, self.th = None, [], False, None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -87,11 +104,33 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((mhz, rs))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.th.join(timeout=1)
+            if not self.samples:
+                return None
+            reasons = sorted(k for k, bit in self.BITS.items() if any(rs & bit for _, rs in self.samples))
+            return dict(sm_mhz=float(np.median([m for m, _ in self.samples])), sm_max_mhz=self.max_mhz,
+                        reasons=reasons, samples=len(self.samples), source="nvml, 2 ms polling")
         if not self.proc:
             return None
         self.proc.terminate()
@@ -116,7 +155,7 @@ class ClockSampler:
         if not sm:
             return None
         return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
-                    samples=len(sm))
+                    samples=len(sm), source="nvidia-smi -lms 100")
 
 
 # ---- FLOP / byte accounting (DESIGN.md section "kernels") ----------------------------------------
@@ -319,7 +358,7 @@ def run_ours(args):
             line_extra["roofline"] = {
                 "kernel": name, "bound": "tensor", "achieved": ach, "peak": peaks["tf_sus"], "unit": "TFLOP/s",
                 "frac": ach / peaks["tf_sus"],
-                "traffic": NCU_TRAFFIC_B32.get(name) if args.math_mode == 2 else None,
+                "traffic": NCU_TRAFFIC_B32.get(name) if args.math_mode >= 2 else None,
                 "traffic_source": "profiles/r01_ncu_umma_full.md (ncu --set full, per launch)",
                 "peak_source": peaks["src"] + " bf16 sustained",
                 "math_mode": MATH_MODES[args.math_mode] + "; achieved = algorithmic 2MNK flops (counted once, "
@@ -333,7 +372,7 @@ def run_ours(args):
             line_extra["roofline_vtrace"] = vtrace_roofline(torch, peaks)
         except Exception as ex:      # pragma: no cover
             line_extra["roofline_vtrace"] = {"error": str(ex)}
-        if args.cpu_baseline:
+        if args.cpu_baseline and world == 1:      # rank 0 at N=1 only
             line_extra["cpu_baseline"] = cpu_reference(3, 1)
     eng.close()
     if rank == 0:
@@ -424,7 +463,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="launch kernels directly instead of CUDA graphs")
-    ap.add_argument("--math-mode", type=int, default=2, choices=[1, 2],
+    ap.add_argument("--math-mode", type=int, default=2, choices=[1, 2, 3],
                     help="1 = FP32 FFMA contractions, 2 = tcgen05 3xTF32 tensor-core contractions (default)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     args = ap.parse_args()

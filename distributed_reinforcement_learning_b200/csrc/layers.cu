@@ -8,6 +8,7 @@
 
 #include "gemm_simt.cuh"
 #include "gemm_umma.cuh"
+#include "gemm_umma_persist.cuh"
 #include "kernels.h"
 #include "loaders.cuh"
 
@@ -60,6 +61,13 @@ using U64 = UmmaCfg<64, 2, 2>;   // 48 KB / stage, 2 CTAs per SM
 using U128 = UmmaCfg<128, 3, 1, 8>;   // 64 KB / stage, 1 CTA per SM, 8 producer warps
 using U256 = UmmaCfg<256, 2, 1, 8>;   // 96 KB / stage, 1 CTA per SM, 8 producer warps
 
+// math mode 3 (experimental): the persistent, fully warp-specialised variant of each tensor-core configuration
+template <class U> struct PersistOf;
+template <> struct PersistOf<U32> { using type = UmmaPCfg<32, 5, 8>; };
+template <> struct PersistOf<U64> { using type = UmmaPCfg<64, 4, 8>; };
+template <> struct PersistOf<U128> { using type = UmmaPCfg<128, 3, 8>; };
+template <> struct PersistOf<U256> { using type = UmmaPCfg<256, 2, 8>; };
+
 static int g_fwd_launches = 0, g_bwd_launches = 0;
 int forward_launch_count() { return g_fwd_launches; }
 int backward_launch_count() { return g_bwd_launches; }
@@ -68,7 +76,9 @@ int backward_launch_count() { return g_bwd_launches; }
 #define GEMM(name, SCfg, UCfg, ...)                          \
   do {                                                       \
     prof_mark(s, name);                                      \
-    if (mode == 2) {                                         \
+    if (mode == 3) {                                         \
+      DRL_TRY((launch_gemm_umma_persist<typename PersistOf<UCfg>::type>(s, __VA_ARGS__))); \
+    } else if (mode == 2) {                                  \
       DRL_TRY((launch_gemm_umma<UCfg>(s, __VA_ARGS__)));     \
     } else {                                                 \
       DRL_TRY((launch_gemm_simt<SCfg>(s, __VA_ARGS__)));     \
@@ -103,19 +113,19 @@ static SplitPlan plan_split(int K, int tiles_mn, int bk, int waves) {
 }
 // the conv weight-gradient plans (mode 1: FFMA tiles, 2 waves; mode 2: 128-row UMMA tiles, 2 CTAs/SM)
 static SplitPlan plan_conv1_wgrad(int Mb, int mode) {
-  return mode == 2 ? plan_split(Mb * 400, 2, 32, 2) : plan_split(Mb * 400, cdiv(256, CfgWg1::BM), 16, 2);
+  return mode >= 2 ? plan_split(Mb * 400, 2, 32, 2) : plan_split(Mb * 400, cdiv(256, CfgWg1::BM), 16, 2);
 }
 static SplitPlan plan_conv2_wgrad(int Mb, int mode) {
-  return mode == 2 ? plan_split(Mb * 81, 4, 32, 2) : plan_split(Mb * 81, cdiv(512, CfgBig::BM), 16, 2);
+  return mode >= 2 ? plan_split(Mb * 81, 4, 32, 2) : plan_split(Mb * 81, cdiv(512, CfgBig::BM), 16, 2);
 }
 static SplitPlan plan_conv3_wgrad(int Mb, int mode) {
-  return mode == 2 ? plan_split(Mb * 49, 5, 32, 2) : plan_split(Mb * 49, cdiv(576, CfgBig::BM), 16, 2);
+  return mode >= 2 ? plan_split(Mb * 49, 5, 32, 2) : plan_split(Mb * 49, cdiv(576, CfgBig::BM), 16, 2);
 }
 
 size_t wgrad_partial_floats(int B, int T) {
   const int Mb = B * (T - 2);
   size_t mx = 0;
-  for (int mode = 1; mode <= 2; ++mode) {
+  for (int mode = 1; mode <= 3; ++mode) {
     mx = std::max(mx, (size_t)plan_conv1_wgrad(Mb, mode).splits * 257 * 32);
     mx = std::max(mx, (size_t)plan_conv2_wgrad(Mb, mode).splits * 513 * 64);
     mx = std::max(mx, (size_t)plan_conv3_wgrad(Mb, mode).splits * 577 * 64);
@@ -180,8 +190,8 @@ int net_forward(const Streams& st, const ParamLayout& pl, const float* P, const 
     PlainB bl{P + pl.lstm_w, Geo::G4, 0};
     EpRaw<false> ep{act.zpart, Geo::G4, (size_t)M * Geo::G4, 1.0f, 0, Geo::G4};
     // FFMA: 4 splits of 57 x 16.  tcgen05: 128 x 256 tiles -> 5 x 4 output tiles x 7 splits of 17 x 32 = 140 CTAs (one wave)
-    nsplit = (mode == 2) ? 7 : 4;
-    const int kchunk = (mode == 2) ? 544 : Geo::XK / 4;
+    nsplit = (mode >= 2) ? 7 : 4;
+    const int kchunk = (mode >= 2) ? 544 : Geo::XK / 4;
     GEMM("lstm_fwd", CfgMid, U256, al, bl, ep, M, Geo::G4, Geo::XK, nsplit, kchunk, kchunk);
   }
   KERNEL("lstm_gates_fwd",
@@ -300,14 +310,16 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, float
     KERNEL("conv3_wgrad_reduce", splitk_reduce(s, bw.wg_part, slab, sp.splits, G + pl.conv3_w, slab), 1);
   }
   s = st.main;
-  if (mode == 2) {
+  if (mode >= 2) {
     // "dCol" form: one plain GEMM with K = 64 output channels (instead of gathering every dY value 9 times
     // through the producers), then a gather of <= 9 taps per input pixel with the ReLU mask.
     PlainA al{bw.da3, 64, 0};
     PlainBT bl{P + pl.conv3_w, 64, 0};               // B(k = co, n = (ky,kx,ci)) = W[n*64 + co]
     EpRaw<false> ep{bw.dcol, 576, 0, 1.0f, 0, 576};
+    // K = 64 (two K tiles) and 128 x 256 outputs per tile: epilogue-dominated, so the persistent kernel with
+    // dedicated epilogue warps wins here (measured 0.067 vs 0.073 ms); elsewhere two CTAs per SM win.
     prof_mark(s, "conv3_dgrad");
-    DRL_TRY((launch_gemm_umma<U256>(s, al, bl, ep, Mb * 49, 576, 64, 1, 64, 0)));
+    DRL_TRY((launch_gemm_umma_persist<PersistOf<U256>::type>(s, al, bl, ep, Mb * 49, 576, 64, 1, 64, 0)));
     DRL_TRY(col2im_conv3(s, bw.dcol, act.a2, bw.da2, Mb));
     n += 2;
   } else {
@@ -329,12 +341,12 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, float
     KERNEL("conv2_wgrad_reduce", splitk_reduce(s, bw.wg_part, slab, sp.splits, G + pl.conv2_w, slab), 1);
   }
   s = st.main;
-  if (mode == 2) {
+  if (mode >= 2) {
     PlainA al{bw.da2, 64, 0};
     PlainBT bl{P + pl.conv2_w, 64, 0};               // B(k = co, n = (ky,kx,ci)) = W[n*64 + co]
     EpRaw<false> ep{bw.dcol, 512, 0, 1.0f, 0, 512};
-    prof_mark(s, "conv2_dgrad");
-    DRL_TRY((launch_gemm_umma<U256>(s, al, bl, ep, Mb * 81, 512, 64, 1, 64, 0)));
+    prof_mark(s, "conv2_dgrad");                      // persistent kernel: 0.079 vs 0.091 ms
+    DRL_TRY((launch_gemm_umma_persist<PersistOf<U256>::type>(s, al, bl, ep, Mb * 81, 512, 64, 1, 64, 0)));
     DRL_TRY(col2im_conv2(s, bw.dcol, act.a1, bw.da1, Mb));
     n += 2;
   } else {

@@ -230,7 +230,7 @@ int drl_learner_create(const drl_learner_config* cfg, drl_learner** out) {
     set_error("reward_clipping must be DRL_REWARD_ABS_ONE or DRL_REWARD_SOFT_ASYMMETRIC");   // utils.py:45
     return DRL_ERR_INVALID;
   }
-  if (cfg->math_mode < 0 || cfg->math_mode > 2) { set_error("math_mode must be 0 (default), 1 (FP32 FFMA) or 2 (tcgen05 3xTF32)"); return DRL_ERR_INVALID; }
+  if (cfg->math_mode < 0 || cfg->math_mode > 3) { set_error("math_mode must be 0 (default), 1 (FP32 FFMA), 2 (tcgen05 3xTF32) or 3 (tcgen05 3xTF32, persistent kernels)"); return DRL_ERR_INVALID; }
   if (drl_device_count() <= cfg->device) { set_error("CUDA device %d not available (no CPU fallback)", cfg->device); return DRL_ERR_CUDA; }
 
   drl_learner* h = new drl_learner();

@@ -84,3 +84,11 @@ def test_step_ragged_shapes_tensor_core_path(native, B, T, A):
 
 def test_two_steps_cuda_graph_tensor_core_path(native):
     _assert_all(parity.compare_step(4, T=20, steps=2, layers=False, use_cuda_graph=True, math_mode=2))
+
+
+@pytest.mark.parametrize("B,T,A,kw", [(4, 20, 18, {}), (32, 20, 18, {"layers": False}), (5, 32, 18, {}), (1, 3, 2, {}),
+                                      (4, 20, 18, {"layers": False, "steps": 2, "use_cuda_graph": True})])
+def test_step_persistent_tensor_core_kernels(native, B, T, A, kw):
+    """math_mode=3: the persistent, fully warp-specialised tcgen05 kernels (dedicated epilogue warps, two TMEM
+    accumulator buffers) reach the same 1e-4 bar."""
+    _assert_all(parity.compare_step(B, T=T, A=A, math_mode=3, **kw))
