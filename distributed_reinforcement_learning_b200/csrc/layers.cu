@@ -56,7 +56,7 @@ using Conv2DA = ConvDgradA<9, 9, 64, 2, 4, 4, 10, 10>;
 using Conv2DB = ConvDgradB<32, 64, 2, 4, 4>;
 using Conv2DE = EpConvDx<20, 20, 32, 2, 10, 10>;
 
-using U32 = UmmaCfg<32, 2, 2>;   // 40 KB / stage (24 KB when A is exact), 2 CTAs per SM
+using U32 = UmmaCfg<32, 2, 3>;   // 24 KB / stage (A exact: conv1 only), 3 CTAs per SM
 using U64 = UmmaCfg<64, 2, 2>;   // 48 KB / stage, 2 CTAs per SM
 using U128 = UmmaCfg<128, 3, 1, 8>;   // 64 KB / stage, 1 CTA per SM, 8 producer warps
 using U256 = UmmaCfg<256, 2, 1, 8>;   // 96 KB / stage, 1 CTA per SM, 8 producer warps
