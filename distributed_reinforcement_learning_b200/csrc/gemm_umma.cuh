@@ -192,6 +192,39 @@ struct loader_vec16 : std::false_type {};
 template <class L>
 struct loader_vec16<L, std::void_t<decltype(L::kVec16)>> : std::bool_constant<L::kVec16> {};
 
+// A B loader may declare `kPretiled`: the operand (a weight matrix) has already been split into hi/lo and stored in
+// global memory as per-(n-tile, k-tile) IMAGES of the shared-memory stage layout (retile_b_kernel below, run once
+// per parameter update).  The producers then do not touch B at all: one thread fetches [B_hi | B_lo] of a stage
+// with a single cp.async.bulk (TMA bulk copy) that completes on the stage's full barrier (complete_tx).
+template <class L, class = void>
+struct loader_pretiled : std::false_type {};
+template <class L>
+struct loader_pretiled<L, std::void_t<decltype(L::kPretiled)>> : std::bool_constant<L::kPretiled> {};
+
+template <class Base>
+struct PretiledB {
+  static constexpr bool kContigK = Base::kContigK;
+  static constexpr bool kPretiled = true;
+  const uint8_t* image;   // [n-tiles][k-tiles][2 * B_BYTES]
+  int ktiles;             // K tiles (of 32) in the image
+  struct Row {};
+  __device__ __forceinline__ Row row(int, int) const { return Row{}; }
+  __device__ __forceinline__ float4 load(const Row&, int) const { return zero4(); }
+};
+
+namespace umma {
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// global -> shared bulk copy (TMA engine), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+}  // namespace umma
+
 template <class Cfg, class AL, class BL>
 struct UmmaSmem {
   using TA = UmmaTile<Cfg::BM, AL::kContigK>;
@@ -214,11 +247,12 @@ gemm_umma_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, int
   constexpr bool AEX = SM::AEX;
   constexpr int NGA = BM * BK / 4, NGB = BN * BK / 4;       // float4 groups per stage
   constexpr bool A16 = loader_vec16<AL>::value;              // 16-element (one 128-bit load) A groups
-  constexpr int GA = (A16 ? NGA / 4 : NGA) / NPROD, GB = NGB / NPROD;   // groups per producer thread
+  constexpr bool BPT = loader_pretiled<BL>::value;           // B arrives as pre-split stage images via cp.async.bulk
+  constexpr int GA = (A16 ? NGA / 4 : NGA) / NPROD, GB = BPT ? 1 : NGB / NPROD;   // groups per producer thread
   static_assert((A16 ? NGA / 4 : NGA) % NPROD == 0 && NGB % NPROD == 0, "groups must divide among producers");
   static_assert(!A16 || AEX, "16-wide raw loads are only used for exact (uint8) operands");
   using ARaw = typename std::conditional<A16, uint4, float4>::type;
-  constexpr bool kColSum = EP::kColSum && !BKc;
+  constexpr bool kColSum = EP::kColSum && !BKc && !BPT;
   constexpr int OFF_ALO = SM::A_BYTES, OFF_BHI = (AEX ? 1 : 2) * SM::A_BYTES, OFF_BLO = OFF_BHI + SM::B_BYTES;
 
   extern __shared__ uint8_t smem_raw[];
@@ -290,7 +324,9 @@ gemm_umma_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, int
 #pragma unroll
     for (int i = 0; i < GB; ++i) {
       const int g = tid + i * NPROD;
-      if (BKc) {
+      if (BPT) {
+        b_k[i] = 0; b_o[i] = 0;
+      } else if (BKc) {
         const int r = g >> 3, kq = g & 7;
         brow[i] = bl.row(z, (n0 + r < N) ? n0 + r : -1);
         b_k[i] = kq * 4;
@@ -315,10 +351,12 @@ gemm_umma_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, int
         if constexpr (A16) ra[i] = (k < k1) ? al.load_raw16(arow[i], k) : make_uint4(0u, 0u, 0u, 0u);
         else ra[i] = (k < k1) ? al.load(arow[i], k) : zero4();
       }
+      if constexpr (!BPT) {
 #pragma unroll
-      for (int i = 0; i < GB; ++i) {
-        const int k = kb + b_k[i];
-        rb[i] = (k < k1) ? bl.load(brow[i], k) : zero4();
+        for (int i = 0; i < GB; ++i) {
+          const int k = kb + b_k[i];
+          rb[i] = (k < k1) ? bl.load(brow[i], k) : zero4();
+        }
       }
     };
     // split tile t into hi/lo and publish it in its shared-memory stage
@@ -327,6 +365,14 @@ gemm_umma_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, int
       const uint32_t ph = (t / STAGES) & 1;
       umma::mbar_wait(&empty[s], ph ^ 1);
       uint8_t* st = smem + s * SM::STAGE_BYTES;
+      if constexpr (BPT) {
+        if (tid == 0) {   // one bulk copy brings [B_hi | B_lo] of this (n-tile, k-tile); bytes complete on full[s]
+          const int kt = (k0 + t * BK) / BK;
+          umma::mbar_expect_tx(&full[s], 2 * SM::B_BYTES);
+          umma::bulk_g2s(st + OFF_BHI, bl.image + ((size_t)blockIdx.y * bl.ktiles + kt) * (size_t)(2 * SM::B_BYTES),
+                         2 * SM::B_BYTES, &full[s]);
+        }
+      }
 #pragma unroll
       for (int i = 0; i < GA; ++i) {
         if constexpr (A16) {
@@ -346,29 +392,38 @@ gemm_umma_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, int
           *reinterpret_cast<float4*>(st + OFF_ALO + a_o[i]) = l;
         }
       }
+      if constexpr (!BPT) {
 #pragma unroll
-      for (int i = 0; i < GB; ++i) {
-        float4 h, l;
-        umma::split4(rb[i], h, l);
-        *reinterpret_cast<float4*>(st + OFF_BHI + b_o[i]) = h;
-        *reinterpret_cast<float4*>(st + OFF_BLO + b_o[i]) = l;
-        if (kColSum) { csum[i].x += rb[i].x; csum[i].y += rb[i].y; csum[i].z += rb[i].z; csum[i].w += rb[i].w; }
+        for (int i = 0; i < GB; ++i) {
+          float4 h, l;
+          umma::split4(rb[i], h, l);
+          *reinterpret_cast<float4*>(st + OFF_BHI + b_o[i]) = h;
+          *reinterpret_cast<float4*>(st + OFF_BLO + b_o[i]) = l;
+          if (kColSum) { csum[i].x += rb[i].x; csum[i].y += rb[i].y; csum[i].z += rb[i].z; csum[i].w += rb[i].w; }
+        }
       }
       umma::fence_proxy_async();       // generic-proxy writes -> visible to the tensor-core (async) proxy
       umma::mbar_arrive(&full[s]);
     };
 
-    // register double buffering: the gathers of tile t+1 are in flight while tile t is split and stored
-    ARaw ra0[GA], ra1[GA];
-    float4 rb0[GB], rb1[GB];
-    if (ntiles > 0) gload(0, ra0, rb0);
+    // register prefetch ring of depth PF: the gathers of tiles t+1 .. t+PF-1 are in flight while tile t is split
+    // and stored (these kernels are bound by per-K-tile latency, not by producer throughput).  The uint8 operand
+    // needs 8 registers per tile, and a pre-tiled B needs none, so those cases afford a deeper ring.
+    constexpr int PF = A16 ? 4 : (BPT ? 3 : 2);
+    ARaw ra[PF][GA];
+    float4 rb[PF][GB];
+#pragma unroll
+    for (int d = 0; d < PF - 1; ++d)
+      if (d < ntiles) gload(d, ra[d], rb[d]);
 #pragma unroll 1
-    for (int t = 0; t < ntiles; t += 2) {
-      if (t + 1 < ntiles) gload(t + 1, ra1, rb1);
-      publish(t, ra0, rb0);
-      if (t + 1 < ntiles) {
-        if (t + 2 < ntiles) gload(t + 2, ra0, rb0);
-        publish(t + 1, ra1, rb1);
+    for (int t0 = 0; t0 < ntiles; t0 += PF) {
+#pragma unroll
+      for (int u = 0; u < PF; ++u) {
+        const int t = t0 + u;
+        if (t < ntiles) {
+          if (t + PF - 1 < ntiles) gload(t + PF - 1, ra[(u + PF - 1) % PF], rb[(u + PF - 1) % PF]);
+          publish(t, ra[u], rb[u]);
+        }
       }
     }
 
@@ -462,6 +517,48 @@ gemm_umma_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, int
     umma::tc_fence_after();
     umma::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
+}
+
+// Writes the pre-split, pre-tiled, pre-swizzled image of a B operand: for every (n-tile, k-tile) the exact bytes the
+// producers would have put into [B_hi | B_lo] of a stage.  Runs once per parameter update.
+template <int BN, class BL>
+__global__ void __launch_bounds__(256) retile_b_kernel(const BL bl, int N, int K, int ktiles, int ntn,
+                                                        uint8_t* __restrict__ image) {
+  using TB = UmmaTile<BN, BL::kContigK>;
+  constexpr int GPT = BN * 8;                         // float4 groups per tile (BN rows x 32 floats)
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long long)ntn * ktiles * GPT) return;
+  const int tile = (int)(g / GPT), lg = (int)(g % GPT);
+  const int nt = tile / ktiles, kt = tile - nt * ktiles;
+  int n, k, off;
+  if (BL::kContigK) {
+    const int r = lg >> 3, kq = lg & 7;
+    n = nt * BN + r; k = kt * 32 + kq * 4; off = TB::chunk_off(r, kq * 4);
+  } else {
+    const int q = lg % (BN / 4), kk = lg / (BN / 4);
+    n = nt * BN + q * 4; k = kt * 32 + kk; off = TB::chunk_off(q * 4, kk);
+  }
+  const typename BL::Row row = bl.row(0, n < N ? n : -1);
+  const float4 v = (k < K) ? bl.load(row, k) : zero4();
+  float4 h, l;
+  umma::split4(v, h, l);
+  uint8_t* dst = image + (size_t)tile * (2 * TB::BYTES);
+  *reinterpret_cast<float4*>(dst + off) = h;
+  *reinterpret_cast<float4*>(dst + TB::BYTES + off) = l;
+}
+
+template <int BN>
+inline size_t weight_image_bytes(int N, int K) {
+  return (size_t)cdiv(N, BN) * cdiv(K, 32) * 2 * BN * 128;
+}
+
+template <int BN, class BL>
+inline int launch_retile_b(cudaStream_t s, const BL& bl, int N, int K, uint8_t* image) {
+  const int ntn = cdiv(N, BN), ktiles = cdiv(K, 32);
+  const long long groups = (long long)ntn * ktiles * BN * 8;
+  retile_b_kernel<BN, BL><<<(unsigned)cdiv64(groups, 256), 256, 0, s>>>(bl, N, K, ktiles, ntn, image);
+  DRL_CHECK_LAUNCH();
+  return DRL_OK;
 }
 
 template <class Cfg, class AL, class BL, class EP>

@@ -43,11 +43,12 @@ gemm_umma_persist_kernel(const AL al, const BL bl, const EP ep, int M, int N, in
   constexpr bool AEX = SM::AEX;
   constexpr bool A16 = loader_vec16<AL>::value;
   constexpr int NGA = BM * BK / 4, NGB = BN * BK / 4;
-  constexpr int GA = (A16 ? NGA / 4 : NGA) / NPROD, GB = NGB / NPROD;
+  constexpr bool BPT = loader_pretiled<BL>::value;
+  constexpr int GA = (A16 ? NGA / 4 : NGA) / NPROD, GB = BPT ? 1 : NGB / NPROD;
   static_assert((A16 ? NGA / 4 : NGA) % NPROD == 0 && NGB % NPROD == 0, "groups must divide among producers");
   static_assert(!A16 || AEX, "16-wide raw loads are only used for exact (uint8) operands");
   using ARaw = typename std::conditional<A16, uint4, float4>::type;
-  constexpr bool kColSum = EP::kColSum && !BKc;
+  constexpr bool kColSum = EP::kColSum && !BKc && !BPT;
   constexpr int OFF_ALO = SM::A_BYTES, OFF_BHI = (AEX ? 1 : 2) * SM::A_BYTES, OFF_BLO = OFF_BHI + SM::B_BYTES;
 
   extern __shared__ uint8_t smem_raw[];
@@ -117,7 +118,8 @@ gemm_umma_persist_kernel(const AL al, const BL bl, const EP ep, int M, int N, in
 #pragma unroll
     for (int i = 0; i < GB; ++i) {
       const int g = tid + i * NPROD;
-      if (BKc) { b_r[i] = g >> 3; b_k[i] = (g & 7) * 4; }
+      if (BPT) { b_r[i] = 0; b_k[i] = 0; }
+      else if (BKc) { b_r[i] = g >> 3; b_k[i] = (g & 7) * 4; }
       else { b_r[i] = (g % (BN / 4)) * 4; b_k[i] = g / (BN / 4); }
       b_o[i] = TB::chunk_off(b_r[i], b_k[i]);
     }
@@ -135,12 +137,14 @@ gemm_umma_persist_kernel(const AL al, const BL bl, const EP ep, int M, int N, in
         if constexpr (A16) ra[i] = (k < p.k1) ? al.load_raw16(row, k) : make_uint4(0u, 0u, 0u, 0u);
         else ra[i] = (k < p.k1) ? al.load(row, k) : zero4();
       }
+      if constexpr (!BPT) {
 #pragma unroll
-      for (int i = 0; i < GB; ++i) {
-        const int n = p.n0 + b_r[i];
-        const typename BL::Row row = bl.row(p.z, n < N ? n : -1);
-        const int k = kb + b_k[i];
-        rb[i] = (k < p.k1) ? bl.load(row, k) : zero4();
+        for (int i = 0; i < GB; ++i) {
+          const int n = p.n0 + b_r[i];
+          const typename BL::Row row = bl.row(p.z, n < N ? n : -1);
+          const int k = kb + b_k[i];
+          rb[i] = (k < p.k1) ? bl.load(row, k) : zero4();
+        }
       }
     };
     auto publish = [&](const PTile& p, int q, const ARaw (&ra)[GA], const float4 (&rb)[GB]) {
@@ -148,6 +152,14 @@ gemm_umma_persist_kernel(const AL al, const BL bl, const EP ep, int M, int N, in
       const uint32_t ph = (q / STAGES) & 1;
       umma::mbar_wait(&empty[s], ph ^ 1);
       uint8_t* st = smem + s * SM::STAGE_BYTES;
+      if constexpr (BPT) {
+        if (tid == 0) {
+          const int kt = (p.k0 + p.t * BK) / BK;
+          umma::mbar_expect_tx(&full[s], 2 * SM::B_BYTES);
+          umma::bulk_g2s(st + OFF_BHI, bl.image + ((size_t)(p.n0 / BN) * bl.ktiles + kt) * (size_t)(2 * SM::B_BYTES),
+                         2 * SM::B_BYTES, &full[s]);
+        }
+      }
 #pragma unroll
       for (int i = 0; i < GA; ++i) {
         if constexpr (A16) {
@@ -168,13 +180,15 @@ gemm_umma_persist_kernel(const AL al, const BL bl, const EP ep, int M, int N, in
         }
       }
       const bool cs_tile = kColSum && p.mt == 0;
+      if constexpr (!BPT) {
 #pragma unroll
-      for (int i = 0; i < GB; ++i) {
-        float4 h, l;
-        umma::split4(rb[i], h, l);
-        *reinterpret_cast<float4*>(st + OFF_BHI + b_o[i]) = h;
-        *reinterpret_cast<float4*>(st + OFF_BLO + b_o[i]) = l;
-        if (cs_tile) { csum[i].x += rb[i].x; csum[i].y += rb[i].y; csum[i].z += rb[i].z; csum[i].w += rb[i].w; }
+        for (int i = 0; i < GB; ++i) {
+          float4 h, l;
+          umma::split4(rb[i], h, l);
+          *reinterpret_cast<float4*>(st + OFF_BHI + b_o[i]) = h;
+          *reinterpret_cast<float4*>(st + OFF_BLO + b_o[i]) = l;
+          if (cs_tile) { csum[i].x += rb[i].x; csum[i].y += rb[i].y; csum[i].z += rb[i].z; csum[i].w += rb[i].w; }
+        }
       }
       umma::fence_proxy_async();
       umma::mbar_arrive(&full[s]);

@@ -90,6 +90,16 @@ constexpr int kLstmSplits = 8;   // slabs allocated for the LSTM split-K partial
 // on the launching stream before each named launch; otherwise it is a no-op.
 void prof_mark(cudaStream_t s, const char* name);
 
+// Pre-split (hi/lo tf32), pre-tiled, pre-swizzled global copies of the weights that serve as B operands of the
+// tensor-core GEMMs (gemm_umma.cuh: PretiledB / retile_b_kernel); refreshed after every parameter update.
+struct WeightImages {
+  static constexpr int kCount = 7;
+  uint8_t* img[kCount];   // 0 conv1 fwd, 1 conv2 fwd, 2 conv3 fwd, 3 lstm fwd, 4 lstm dgrad, 5 conv3 dCol, 6 conv2 dCol
+};
+void weight_image_sizes(size_t (&bytes)[WeightImages::kCount]);
+int net_retile(cudaStream_t s_conv, cudaStream_t s_rest, const ParamLayout& pl, const float* params,
+               const WeightImages& wi);
+
 // ---- layers.cu ----------------------------------------------------------------------------
 // main = critical path; side = kernels off the critical path (fork/join through ev[]); par = false runs
 // everything on main (used by the per-kernel profile so that event times are per-kernel).
@@ -99,10 +109,10 @@ struct Streams {
   bool par;
 };
 // mode: 1 = FP32-FFMA gather-GEMM, 2 = tcgen05 3xTF32 gather-GEMM for the large contractions
-int net_forward(const Streams& st, const ParamLayout& pl, const float* params, const Inputs& in, const Acts& act,
-                int B, int T, int mode);
-int net_backward(const Streams& st, const ParamLayout& pl, const float* params, float* grads, const Inputs& in,
-                 const Acts& act, const Bwd& bwd, int B, int T, int mode);
+int net_forward(const Streams& st, const ParamLayout& pl, const float* params, const WeightImages& wi, const Inputs& in,
+                const Acts& act, int B, int T, int mode, bool retile);
+int net_backward(const Streams& st, const ParamLayout& pl, const float* params, const WeightImages& wi, float* grads,
+                 const Inputs& in, const Acts& act, const Bwd& bwd, int B, int T, int mode);
 size_t wgrad_partial_floats(int B, int T);
 int forward_launch_count();
 int backward_launch_count();

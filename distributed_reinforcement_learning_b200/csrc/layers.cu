@@ -85,6 +85,19 @@ int backward_launch_count() { return g_bwd_launches; }
     }                                                        \
     ++n;                                                     \
   } while (0)
+// same, for GEMMs whose B operand is a weight matrix: the tensor-core cores read its pre-tiled image (blp)
+#define GEMM_W(name, SCfg, UCfg, al, bl, blp, ...)            \
+  do {                                                       \
+    prof_mark(s, name);                                      \
+    if (mode == 3) {                                         \
+      DRL_TRY((launch_gemm_umma_persist<typename PersistOf<UCfg>::type>(s, al, blp, __VA_ARGS__))); \
+    } else if (mode == 2) {                                  \
+      DRL_TRY((launch_gemm_umma<UCfg>(s, al, blp, __VA_ARGS__))); \
+    } else {                                                 \
+      DRL_TRY((launch_gemm_simt<SCfg>(s, al, bl, __VA_ARGS__))); \
+    }                                                        \
+    ++n;                                                     \
+  } while (0)
 #define GEMM_FFMA(name, SCfg, ...)                           \
   do {                                                       \
     prof_mark(s, name);                                      \
@@ -133,6 +146,28 @@ size_t wgrad_partial_floats(int B, int T) {
   return std::max(mx, (size_t)16 * 32 * 256);   // also the scratch of emb_backward (kEmbChunks * A * 256)
 }
 
+void weight_image_sizes(size_t (&b)[WeightImages::kCount]) {
+  b[0] = weight_image_bytes<32>(32, 256);
+  b[1] = weight_image_bytes<64>(64, 512);
+  b[2] = weight_image_bytes<64>(64, 576);
+  b[3] = weight_image_bytes<256>(Geo::G4, Geo::XK);
+  b[4] = weight_image_bytes<128>(Geo::FLAT + Geo::EMB, Geo::G4);
+  b[5] = weight_image_bytes<256>(576, 64);
+  b[6] = weight_image_bytes<256>(512, 64);
+}
+
+// Refresh the weight images (7 small launches; ~60 MB written).  Must run after every parameter change.
+// Only the big weight operands are pre-tiled (LSTM forward/dgrad, the dCol GEMMs): for the conv-forward GEMMs the
+// weight tile is a small part of a stage and pre-tiling it measured no gain (images 0-2 stay unused).
+int net_retile(cudaStream_t, cudaStream_t s_rest, const ParamLayout& pl, const float* P, const WeightImages& wi) {
+  prof_mark(s_rest, "weight_retile");
+  DRL_TRY((launch_retile_b<256>(s_rest, PlainB{P + pl.lstm_w, Geo::G4, 0}, Geo::G4, Geo::XK, wi.img[3])));
+  DRL_TRY((launch_retile_b<128>(s_rest, PlainBT{P + pl.lstm_w, Geo::G4, 0}, Geo::FLAT + Geo::EMB, Geo::G4, wi.img[4])));
+  DRL_TRY((launch_retile_b<256>(s_rest, PlainBT{P + pl.conv3_w, 64, 0}, 576, 64, wi.img[5])));
+  DRL_TRY((launch_retile_b<256>(s_rest, PlainBT{P + pl.conv2_w, 64, 0}, 512, 64, wi.img[6])));
+  return DRL_OK;
+}
+
 // Fork/join helpers: kernels that are off the critical path (the action-embedding table in the forward, every
 // weight gradient except conv1's in the backward) run on the side stream so they fill SMs the critical
 // dgrad chain leaves idle.  Inside CUDA-graph capture the event record/wait pairs become graph edges.
@@ -149,8 +184,8 @@ static int join_from_side(const Streams& st, int i) {
   return DRL_OK;
 }
 
-int net_forward(const Streams& st, const ParamLayout& pl, const float* P, const Inputs& in, const Acts& act, int B,
-                int T, int mode) {
+int net_forward(const Streams& st, const ParamLayout& pl, const float* P, const WeightImages& wi, const Inputs& in,
+                const Acts& act, int B, int T, int mode, bool retile) {
   const int M = B * T;
   const RowMap map{B, T};
   int n = 0, nsplit = 4;
@@ -162,6 +197,12 @@ int net_forward(const Streams& st, const ParamLayout& pl, const float* P, const 
   KERNEL("emb_fwd",
          emb_forward(s, P + pl.emb1_w, P + pl.emb1_b, P + pl.emb2_w, P + pl.emb2_b, act.e1, act.table, pl.A), 1);
   s = st.main;
+  // weight images of this step's parameters: the conv-forward ones on the main stream (needed at once), the LSTM /
+  // dgrad ones behind the embedding table on the side stream, hidden under the conv forward (joined before lstm_fwd)
+  if (retile && mode >= 2) {
+    DRL_TRY(net_retile(st.main, side, pl, P, wi));
+    n += 4;
+  }
   // conv1: u8 frames -> a1 [M,20,20,32]   (attention_CNN, model/impala_actor_critic.py:6)
   {
     Conv1A al{in.frames, map};
@@ -192,7 +233,8 @@ int net_forward(const Streams& st, const ParamLayout& pl, const float* P, const 
     // FFMA: 4 splits of 57 x 16.  tcgen05: 128 x 256 tiles -> 5 x 4 output tiles x 7 splits of 17 x 32 = 140 CTAs (one wave)
     nsplit = (mode >= 2) ? 7 : 4;
     const int kchunk = (mode >= 2) ? 544 : Geo::XK / 4;
-    GEMM("lstm_fwd", CfgMid, U256, al, bl, ep, M, Geo::G4, Geo::XK, nsplit, kchunk, kchunk);
+    PretiledB<PlainB> blp{wi.img[3], Geo::XK / 32};
+    GEMM_W("lstm_fwd", CfgMid, U256, al, bl, blp, ep, M, Geo::G4, Geo::XK, nsplit, kchunk, kchunk);
   }
   KERNEL("lstm_gates_fwd",
          lstm_gates_forward(s, act.zpart, nsplit, P + pl.lstm_b, in.c0, act.gates, act.c1, act.tc1, act.h1, M, B,
@@ -218,8 +260,8 @@ int net_forward(const Streams& st, const ParamLayout& pl, const float* P, const 
   return DRL_OK;
 }
 
-int net_backward(const Streams& st, const ParamLayout& pl, const float* P, float* G, const Inputs& in, const Acts& act,
-                 const Bwd& bw, int B, int T, int mode) {
+int net_backward(const Streams& st, const ParamLayout& pl, const float* P, const WeightImages& wi, float* G,
+                 const Inputs& in, const Acts& act, const Bwd& bw, int B, int T, int mode) {
   cudaStream_t s = st.main;
   const cudaStream_t side = st.par ? st.side : st.main;
   const int M = B * T;
@@ -291,7 +333,8 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, float
     PlainA al{bw.dz, Geo::G4, 0};
     PlainBT bl{P + pl.lstm_w, Geo::G4, 0};
     EpLstmDx ep{bw.da3, act.a3, bw.du};
-    GEMM("lstm_dgrad", CfgMid, U128, al, bl, ep, Mb, Geo::FLAT + Geo::EMB, Geo::G4, 1, Geo::G4, 0);
+    PretiledB<PlainBT> blp{wi.img[4], Geo::G4 / 32};
+    GEMM_W("lstm_dgrad", CfgMid, U128, al, bl, blp, ep, Mb, Geo::FLAT + Geo::EMB, Geo::G4, 1, Geo::G4, 0);
   }
   // ---- action embedding + conv3 weight gradient (side) -------------------------------------
   DRL_TRY(fork_to_side(st, 4));
@@ -319,7 +362,8 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, float
     // K = 64 (two K tiles) and 128 x 256 outputs per tile: epilogue-dominated, so the persistent kernel with
     // dedicated epilogue warps wins here (measured 0.067 vs 0.073 ms); elsewhere two CTAs per SM win.
     prof_mark(s, "conv3_dgrad");
-    DRL_TRY((launch_gemm_umma_persist<PersistOf<U256>::type>(s, al, bl, ep, Mb * 49, 576, 64, 1, 64, 0)));
+    PretiledB<PlainBT> blp{wi.img[5], 2};
+    DRL_TRY((launch_gemm_umma_persist<PersistOf<U256>::type>(s, al, blp, ep, Mb * 49, 576, 64, 1, 64, 0)));
     DRL_TRY(col2im_conv3(s, bw.dcol, act.a2, bw.da2, Mb));
     n += 2;
   } else {
@@ -346,7 +390,8 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, float
     PlainBT bl{P + pl.conv2_w, 64, 0};               // B(k = co, n = (ky,kx,ci)) = W[n*64 + co]
     EpRaw<false> ep{bw.dcol, 512, 0, 1.0f, 0, 512};
     prof_mark(s, "conv2_dgrad");                      // persistent kernel: 0.079 vs 0.091 ms
-    DRL_TRY((launch_gemm_umma_persist<PersistOf<U256>::type>(s, al, bl, ep, Mb * 81, 512, 64, 1, 64, 0)));
+    PretiledB<PlainBT> blp{wi.img[6], 2};
+    DRL_TRY((launch_gemm_umma_persist<PersistOf<U256>::type>(s, al, blp, ep, Mb * 81, 512, 64, 1, 64, 0)));
     DRL_TRY(col2im_conv2(s, bw.dcol, act.a1, bw.da1, Mb));
     n += 2;
   } else {

@@ -56,11 +56,13 @@ struct drl_learner {
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done = nullptr;
   cudaEvent_t fj[8] = {};    // fork/join events between the compute and the side stream
   bool par = true;           // run off-critical-path kernels on the side stream
+  bool images_stale = true;  // weight images do not match the parameters (forward-only entry points rebuild them)
   float* params = nullptr;
   float* ms = nullptr;
   float* bucket = nullptr;   // [padded_total grads | 4 loss sums]
   Acts act{};
   Bwd bwd{};
+  WeightImages wimg{};
   VtraceOut vt{};
   OptState opt{};
   long long* d_step = nullptr;
@@ -129,18 +131,20 @@ Streams streams_of(const drl_learner* h) {
   return st;
 }
 
-int enqueue_forward(drl_learner* h, const Inputs& in, int B, int T) {
-  return net_forward(streams_of(h), h->pl, h->params, in, h->act, B, T, h->mode);
+// retile = true: (re)build the weight images first.  A training step always does (the parameters changed in the
+// previous apply); the forward-only entry points only when the images are stale.
+int enqueue_forward(drl_learner* h, const Inputs& in, int B, int T, bool retile) {
+  return net_forward(streams_of(h), h->pl, h->params, h->wimg, in, h->act, B, T, h->mode, retile);
 }
 
 int enqueue_forward_backward(drl_learner* h, int slot) {
   const Inputs& in = h->slots[slot].in;
-  DRL_TRY(enqueue_forward(h, in, h->B, h->T));
+  DRL_TRY(enqueue_forward(h, in, h->B, h->T, true));
   VtraceCfg vc{h->cfg.discount_factor, h->cfg.baseline_loss_coef, h->cfg.entropy_coef, h->cfg.reward_clipping};
   prof_mark(h->compute, "vtrace_losses");
   DRL_TRY(vtrace_losses(h->compute, vc, h->act.policy, h->act.value, in, h->vt, h->bwd.dlogits, h->bwd.dv, h->B,
                         h->T, h->A));
-  DRL_TRY(net_backward(streams_of(h), h->pl, h->params, h->bucket, in, h->act, h->bwd, h->B, h->T, h->mode));
+  DRL_TRY(net_backward(streams_of(h), h->pl, h->params, h->wimg, h->bucket, in, h->act, h->bwd, h->B, h->T, h->mode));
   return DRL_OK;
 }
 
@@ -198,6 +202,7 @@ int run_apply(drl_learner* h) {
   DRL_CUDA_CHECK(cudaEventRecord(h->ev_stop, h->compute));
   DRL_CUDA_CHECK(cudaEventRecord(h->ev_done, h->compute));
   h->pending = true;
+  h->images_stale = true;
   return DRL_OK;
 }
 
@@ -290,6 +295,11 @@ int drl_learner_create(const drl_learner_config* cfg, drl_learner** out) {
     DRL_TRY(dev_alloc(h, &b.wg_part, b.wg_part_floats));
     DRL_TRY(dev_alloc(h, &b.wg_part2, b.wg_part_floats));
     DRL_TRY(dev_alloc(h, &b.dcol, Mb * 81 * 512));
+    {
+      size_t wb[WeightImages::kCount];
+      weight_image_sizes(wb);
+      for (int i = 0; i < WeightImages::kCount; ++i) DRL_TRY(dev_alloc(h, &h->wimg.img[i], wb[i]));
+    }
     VtraceOut& v = h->vt;
     const size_t nt = (size_t)h->B * (h->T - 2);
     DRL_TRY(dev_alloc(h, &v.vs, nt));
@@ -387,7 +397,9 @@ int drl_learner_set_params(drl_learner* h, const float* host_flat, int64_t n) {
   DRL_TRY(check_handle(h));
   if (!host_flat || n != h->pl.packed_total) { set_error("set_params: expected %lld floats, got %lld", (long long)h->pl.packed_total, (long long)n); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
-  return upload_flat(h, h->params, host_flat, 0.0f);
+  DRL_TRY(upload_flat(h, h->params, host_flat, 0.0f));
+  h->images_stale = true;
+  return DRL_OK;
 }
 int drl_learner_get_params(drl_learner* h, float* host_flat, int64_t n) {
   DRL_TRY(check_handle(h));
@@ -519,7 +531,8 @@ int drl_learner_forward(drl_learner* h, int32_t slot, float* policy, float* valu
   Slot& s = h->slots[slot];
   if (!s.has_data) { set_error("slot %d has not been staged", slot); return DRL_ERR_STATE; }
   DRL_CUDA_CHECK(cudaStreamWaitEvent(h->compute, s.staged, 0));
-  DRL_TRY(enqueue_forward(h, s.in, h->B, h->T));
+  DRL_TRY(enqueue_forward(h, s.in, h->B, h->T, h->images_stale));
+  h->images_stale = false;
   DRL_CUDA_CHECK(cudaEventRecord(s.consumed, h->compute));
   // time-major device rows -> batch-major host arrays
   const int B = h->B, T = h->T, A = h->A;
@@ -594,7 +607,8 @@ int drl_learner_act(drl_learner* h, int32_t n, const uint8_t* state, const int32
   DRL_CUDA_CHECK(cp(s.in.h0, h_in, (size_t)n * Geo::L * 4));
   DRL_CUDA_CHECK(cp(s.in.c0, c_in, (size_t)n * Geo::L * 4));
   s.has_data = false;   // the slot no longer holds a training batch
-  DRL_TRY(enqueue_forward(h, s.in, n, 1));
+  DRL_TRY(enqueue_forward(h, s.in, n, 1, h->images_stale));
+  h->images_stale = false;
   if (policy) DRL_CUDA_CHECK(cudaMemcpyAsync(policy, h->act.policy, (size_t)n * h->A * 4, cudaMemcpyDeviceToHost, h->compute));
   if (h_out) DRL_CUDA_CHECK(cudaMemcpyAsync(h_out, h->act.h1, (size_t)n * Geo::L * 4, cudaMemcpyDeviceToHost, h->compute));
   if (c_out) DRL_CUDA_CHECK(cudaMemcpyAsync(c_out, h->act.c1, (size_t)n * Geo::L * 4, cudaMemcpyDeviceToHost, h->compute));
