@@ -17,6 +17,7 @@ namespace drl {
 __global__ void __launch_bounds__(256) emb_forward_kernel(const float* __restrict__ w1, const float* __restrict__ b1,
                                                            const float* __restrict__ w2, const float* __restrict__ b2,
                                                            float* __restrict__ e1, float* __restrict__ table) {
+  pdl_prologue();
   __shared__ float se[Geo::EMB];
   __shared__ float part[4][64];
   const int a = blockIdx.x, tid = threadIdx.x;
@@ -42,8 +43,7 @@ __global__ void __launch_bounds__(256) emb_forward_kernel(const float* __restric
 
 int emb_forward(cudaStream_t s, const float* w1, const float* b1, const float* w2, const float* b2, float* e1,
                 float* table, int A) {
-  emb_forward_kernel<<<dim3(A, 4), 256, 0, s>>>(w1, b1, w2, b2, e1, table);
-  DRL_CHECK_LAUNCH();
+  DRL_CUDA_CHECK((launch_k(emb_forward_kernel, dim3(A, 4), 256, 0, s, w1, b1, w2, b2, e1, table)));
   return DRL_OK;
 }
 
@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(256) lstm_gates_forward_kernel(
     const float* __restrict__ zpart, int nsplit, size_t split_stride, const float* __restrict__ bias,
     const float* __restrict__ c0, float* __restrict__ gates, float* __restrict__ c1, float* __restrict__ tc1,
     float* __restrict__ h1, int M, int B, int T) {
+  pdl_prologue();
   const int m = blockIdx.x, u = threadIdx.x;
   if (m >= M) return;
   const int t = m / B, b = m - t * B;
@@ -82,9 +83,8 @@ __global__ void __launch_bounds__(256) lstm_gates_forward_kernel(
 
 int lstm_gates_forward(cudaStream_t s, const float* zpart, int nsplit, const float* bias, const float* c0,
                        float* gates, float* c1, float* tc1, float* h1, int M, int B, int T) {
-  lstm_gates_forward_kernel<<<M, 256, 0, s>>>(zpart, nsplit, (size_t)M * Geo::G4, bias, c0, gates, c1, tc1, h1, M, B,
-                                              T);
-  DRL_CHECK_LAUNCH();
+  DRL_CUDA_CHECK((launch_k(lstm_gates_forward_kernel, M, 256, 0, s, zpart, nsplit, (size_t)M * Geo::G4, bias, c0, gates, c1, tc1, h1, M, B,
+                                              T)));
   return DRL_OK;
 }
 
@@ -93,6 +93,7 @@ int lstm_gates_forward(cudaStream_t s, const float* zpart, int nsplit, const flo
 __global__ void __launch_bounds__(256) lstm_gates_backward_kernel(
     const float* __restrict__ dh_part, size_t part_stride, const float* __restrict__ gates,
     const float* __restrict__ tc1, const float* __restrict__ c0, float* __restrict__ dz, int Mb, int B, int T) {
+  pdl_prologue();
   const int m = blockIdx.x, u = threadIdx.x;
   if (m >= Mb) return;
   const int t = m / B, b = m - t * B;
@@ -113,8 +114,7 @@ __global__ void __launch_bounds__(256) lstm_gates_backward_kernel(
 
 int lstm_gates_backward(cudaStream_t s, const float* dh_part, size_t part_stride, const float* gates,
                         const float* tc1, const float* c0, float* dz, int Mb, int B, int T) {
-  lstm_gates_backward_kernel<<<Mb, 256, 0, s>>>(dh_part, part_stride, gates, tc1, c0, dz, Mb, B, T);
-  DRL_CHECK_LAUNCH();
+  DRL_CUDA_CHECK((launch_k(lstm_gates_backward_kernel, Mb, 256, 0, s, dh_part, part_stride, gates, tc1, c0, dz, Mb, B, T)));
   return DRL_OK;
 }
 
@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(128) heads_out_forward_kernel(
     const float* __restrict__ ha, const float* __restrict__ hc, const float* __restrict__ w5,
     const float* __restrict__ b5, const float* __restrict__ w8, const float* __restrict__ b8,
     float* __restrict__ logits, float* __restrict__ policy, float* __restrict__ value, int M, int A) {
+  pdl_prologue();
   extern __shared__ float sw[];   // W5 [256*A] then w8 [256]
   for (int i = threadIdx.x; i < Geo::HID * A; i += blockDim.x) sw[i] = w5[i];
   for (int i = threadIdx.x; i < Geo::HID; i += blockDim.x) sw[Geo::HID * A + i] = w8[i];
@@ -171,8 +172,7 @@ int heads_out_forward(cudaStream_t s, const float* ha, const float* hc, const fl
                       const float* w8, const float* b8, float* logits, float* policy, float* value, int M, int A) {
   if (A > kMaxA) { set_error("num_action %d > %d unsupported", A, kMaxA); return DRL_ERR_INVALID; }
   const size_t smem = (size_t)(Geo::HID * A + Geo::HID) * sizeof(float);
-  heads_out_forward_kernel<<<cdiv(M, 4), 128, smem, s>>>(ha, hc, w5, b5, w8, b8, logits, policy, value, M, A);
-  DRL_CHECK_LAUNCH();
+  DRL_CUDA_CHECK((launch_k(heads_out_forward_kernel, cdiv(M, 4), 128, smem, s, ha, hc, w5, b5, w8, b8, logits, policy, value, M, A)));
   return DRL_OK;
 }
 
@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(256) heads_out_backward_kernel(
     const float* __restrict__ dlogits, const float* __restrict__ dv, const float* __restrict__ w5,
     const float* __restrict__ w8, const float* __restrict__ ha, const float* __restrict__ hc,
     float* __restrict__ dha, float* __restrict__ dhc, int Mb, int A) {
+  pdl_prologue();
   __shared__ float sd[kMaxA];
   __shared__ float sdv;
   const int m = blockIdx.x, k = threadIdx.x;
@@ -197,8 +198,7 @@ __global__ void __launch_bounds__(256) heads_out_backward_kernel(
 
 int heads_out_backward(cudaStream_t s, const float* dlogits, const float* dv, const float* w5, const float* w8,
                        const float* ha, const float* hc, float* dha, float* dhc, int Mb, int A) {
-  heads_out_backward_kernel<<<Mb, 256, 0, s>>>(dlogits, dv, w5, w8, ha, hc, dha, dhc, Mb, A);
-  DRL_CHECK_LAUNCH();
+  DRL_CUDA_CHECK((launch_k(heads_out_backward_kernel, Mb, 256, 0, s, dlogits, dv, w5, w8, ha, hc, dha, dhc, Mb, A)));
   return DRL_OK;
 }
 
@@ -211,6 +211,7 @@ int heads_out_backward(cudaStream_t s, const float* dlogits, const float* dv, co
 constexpr int kEmbChunks = 16;
 __global__ void __launch_bounds__(256) emb_segsum_kernel(const float* __restrict__ du, const int32_t* __restrict__ pa,
                                                           float* __restrict__ part, int Mb, int B, int T, int A) {
+  pdl_prologue();
   const int a = blockIdx.x, c = blockIdx.y, j = threadIdx.x;
   const int per = (Mb + kEmbChunks - 1) / kEmbChunks;
   const int lo = c * per, hi = min(Mb, lo + per);
@@ -224,6 +225,7 @@ __global__ void __launch_bounds__(256) emb_segsum_kernel(const float* __restrict
 // (1b) dpre2[a,j] = relu'(table[a,j]) * sum_c part[c][a][j]   (fixed order)           grid A, 256 threads
 __global__ void __launch_bounds__(256) emb_dpre2_kernel(const float* __restrict__ part, const float* __restrict__ table,
                                                          float* __restrict__ dpre2, int A) {
+  pdl_prologue();
   const int a = blockIdx.x, j = threadIdx.x;
   float acc = 0.f;
 #pragma unroll
@@ -233,6 +235,7 @@ __global__ void __launch_bounds__(256) emb_dpre2_kernel(const float* __restrict_
 // (2) g_w2[k,j] = sum_a e1[a,k] dpre2[a,j] ; g_b2[j] = sum_a dpre2[a,j]             grid 256 (k), 256 threads (j)
 __global__ void __launch_bounds__(256) emb_bwd2_kernel(const float* __restrict__ e1, const float* __restrict__ dpre2,
                                                         float* __restrict__ g_w2, float* __restrict__ g_b2, int A) {
+  pdl_prologue();
   const int k = blockIdx.x, j = threadIdx.x;
   float acc = 0.f, bs = 0.f;
   for (int a = 0; a < A; ++a) {
@@ -248,6 +251,7 @@ __global__ void __launch_bounds__(256) emb_bwd2_kernel(const float* __restrict__
 __global__ void __launch_bounds__(256) emb_bwd1_kernel(const float* __restrict__ e1, const float* __restrict__ dpre2,
                                                         const float* __restrict__ w2, float* __restrict__ dpre1,
                                                         float* __restrict__ g_w1, float* __restrict__ g_b1, int A) {
+  pdl_prologue();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k = blockIdx.x * 8 + warp;
   float w[8];
@@ -273,14 +277,10 @@ int emb_backward(cudaStream_t s, const float* du, const int32_t* pa, const float
                  const float* w2, float* dpre2, float* dpre1, float* g_w1, float* g_b1, float* g_w2, float* g_b2,
                  float* scratch, int Mb, int B, int T, int A) {
   // scratch: >= kEmbChunks * A * 256 floats (the split-K partial buffer, idle at this point of the step)
-  emb_segsum_kernel<<<dim3(A, kEmbChunks), 256, 0, s>>>(du, pa, scratch, Mb, B, T, A);
-  DRL_CHECK_LAUNCH();
-  emb_dpre2_kernel<<<A, 256, 0, s>>>(scratch, table, dpre2, A);
-  DRL_CHECK_LAUNCH();
-  emb_bwd2_kernel<<<Geo::EMB, 256, 0, s>>>(e1, dpre2, g_w2, g_b2, A);
-  DRL_CHECK_LAUNCH();
-  emb_bwd1_kernel<<<Geo::EMB / 8, 256, 0, s>>>(e1, dpre2, w2, dpre1, g_w1, g_b1, A);
-  DRL_CHECK_LAUNCH();
+  DRL_CUDA_CHECK((launch_k(emb_segsum_kernel, dim3(A, kEmbChunks), 256, 0, s, du, pa, scratch, Mb, B, T, A)));
+  DRL_CUDA_CHECK((launch_k(emb_dpre2_kernel, A, 256, 0, s, scratch, table, dpre2, A)));
+  DRL_CUDA_CHECK((launch_k(emb_bwd2_kernel, Geo::EMB, 256, 0, s, e1, dpre2, g_w2, g_b2, A)));
+  DRL_CUDA_CHECK((launch_k(emb_bwd1_kernel, Geo::EMB / 8, 256, 0, s, e1, dpre2, w2, dpre1, g_w1, g_b1, A)));
   return DRL_OK;
 }
 
@@ -294,6 +294,7 @@ template <int IH, int IW, int CI, int OH, int OW, int KH, int KW, int S>
 __global__ void __launch_bounds__(256) col2im_relu_kernel(const float* __restrict__ dcol,
                                                            const float* __restrict__ act, float* __restrict__ dx,
                                                            int nimg) {
+  pdl_prologue();
   constexpr int C4 = CI / 4, NCOL = KH * KW * CI;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)nimg * IH * IW * C4;
@@ -327,14 +328,12 @@ __global__ void __launch_bounds__(256) col2im_relu_kernel(const float* __restric
 
 int col2im_conv3(cudaStream_t s, const float* dcol, const float* a2, float* da2, int nimg) {
   const long long total = (long long)nimg * 9 * 9 * 16;
-  col2im_relu_kernel<9, 9, 64, 7, 7, 3, 3, 1><<<(unsigned)cdiv64(total, 256), 256, 0, s>>>(dcol, a2, da2, nimg);
-  DRL_CHECK_LAUNCH();
+  DRL_CUDA_CHECK((launch_k(col2im_relu_kernel<9, 9, 64, 7, 7, 3, 3, 1>, (unsigned)cdiv64(total, 256), 256, 0, s, dcol, a2, da2, nimg)));
   return DRL_OK;
 }
 int col2im_conv2(cudaStream_t s, const float* dcol, const float* a1, float* da1, int nimg) {
   const long long total = (long long)nimg * 20 * 20 * 8;
-  col2im_relu_kernel<20, 20, 32, 9, 9, 4, 4, 2><<<(unsigned)cdiv64(total, 256), 256, 0, s>>>(dcol, a1, da1, nimg);
-  DRL_CHECK_LAUNCH();
+  DRL_CUDA_CHECK((launch_k(col2im_relu_kernel<20, 20, 32, 9, 9, 4, 4, 2>, (unsigned)cdiv64(total, 256), 256, 0, s, dcol, a1, da1, nimg)));
   return DRL_OK;
 }
 
@@ -343,6 +342,7 @@ int col2im_conv2(cudaStream_t s, const float* dcol, const float* a1, float* da1,
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, size_t slab, int nsplit,
                                                              float* __restrict__ out, size_t n) {
+  pdl_prologue();
   const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -358,8 +358,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
 }
 
 int splitk_reduce(cudaStream_t s, const float* part, size_t slab, int nsplit, float* out, size_t n) {
-  splitk_reduce_kernel<<<(unsigned)cdiv64((int64_t)n, 256), 256, 0, s>>>(part, slab, nsplit, out, n);
-  DRL_CHECK_LAUNCH();
+  DRL_CUDA_CHECK((launch_k(splitk_reduce_kernel, (unsigned)cdiv64((int64_t)n, 256), 256, 0, s, part, slab, nsplit, out, n)));
   return DRL_OK;
 }
 

@@ -46,6 +46,7 @@ struct SmemLayout {
 template <class Cfg, class AL, class BL, class EP>
 __global__ void __launch_bounds__(Cfg::NT)
 gemm_simt_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, int kchunk, int kstep) {
+  pdl_prologue();
   constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, TM = Cfg::TM, TN = Cfg::TN;
   constexpr int NT = Cfg::NT, TX = Cfg::TX, QM = Cfg::QM, QN = Cfg::QN;
   constexpr bool AK = AL::kContigK, BKc = BL::kContigK;
@@ -254,8 +255,7 @@ inline int launch_gemm_simt(cudaStream_t s, const AL& al, const BL& bl, const EP
     return DRL_ERR_INVALID;
   }
   dim3 grid(cdiv(M, Cfg::BM), cdiv(N, Cfg::BN), zcount);
-  kern<<<grid, Cfg::NT, SL::BYTES, s>>>(al, bl, ep, M, N, K, kchunk, kstep);
-  DRL_CHECK_LAUNCH();
+  DRL_CUDA_CHECK((launch_k(kern, grid, Cfg::NT, SL::BYTES, s, al, bl, ep, M, N, K, kchunk, kstep)));
   return DRL_OK;
 }
 

@@ -225,6 +225,43 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 }
 }  // namespace umma
 
+// Epilogue store of one 32x32 accumulator block.  tcgen05.ld hands every lane one ROW (v[j] = D[row0 + lane][col0 + j]);
+// storing that directly makes each 128-bit store instruction touch 32 different 128-byte lines (ncu: the LSU data
+// pipe was the busiest unit of the epilogue-heavy kernels).  The block is transposed through a per-warp 4 KB
+// shared-memory tile instead (16-byte chunks XOR-swizzled by row & 7: conflict-free both ways), so that 8 lanes
+// cover one 128-byte row segment and an instruction touches 4 lines.  The functor sees the same (m, n) pairs.
+constexpr int kEpiStageBytes = 32 * 32 * 4;
+template <class EP>
+__device__ __forceinline__ void epilogue_store_32x32(const EP& ep, uint8_t* stg, int lane, int z, int row0, int col0,
+                                                     int M, int N, const float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+        make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  __syncwarp();
+  const int c = lane & 7, rr = lane >> 3;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + rr;
+    const float4 o4 = *reinterpret_cast<const float4*>(stg + r * 128 + ((c ^ (r & 7)) << 4));
+    const int m = row0 + r, n = col0 + c * 4;
+    if (m < M) {
+      const float o[4] = {o4.x, o4.y, o4.z, o4.w};
+      if (n + 3 < N) {
+        ep.template store<4>(z, m, n, o);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (n + q < N) {
+            const float o1[1] = {o[q]};
+            ep.template store<1>(z, m, n + q, o1);
+          }
+      }
+    }
+  }
+  __syncwarp();
+}
+
 template <class Cfg, class AL, class BL>
 struct UmmaSmem {
   using TA = UmmaTile<Cfg::BM, AL::kContigK>;
@@ -239,6 +276,7 @@ struct UmmaSmem {
 template <class Cfg, class AL, class BL, class EP>
 __global__ void __launch_bounds__(Cfg::NT, Cfg::MINB)
 gemm_umma_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, int kchunk, int kstep) {
+  pdl_prologue();
   constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES, NPROD = Cfg::NPROD;
   constexpr bool AK = AL::kContigK, BKc = BL::kContigK;
   using SM = UmmaSmem<Cfg, AL, BL>;
@@ -452,30 +490,16 @@ gemm_umma_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, int
     // ================= EPILOGUE =================
     umma::mbar_wait(acc_full, 0);
     umma::tc_fence_after();
-    // warp w may only touch TMEM lanes 32*(w%4)..+31; with 8 warps the two warps of a lane quarter split the columns
-    const int m = m0 + (warp & 3) * 32 + lane;
+    // warp w may only touch TMEM lanes 32*(w%4)..+31; with 8 warps the two warps of a lane quarter split the columns.
+    // Every MMA has completed, so the pipeline stages are dead: their first bytes become the per-warp staging tiles.
+    uint8_t* stg = smem + warp * kEpiStageBytes;
+    const int row0 = m0 + (warp & 3) * 32;
     const int cbeg = (warp >> 2) * Cfg::EPI_COLS;
 #pragma unroll 1
     for (int c0 = cbeg; c0 < cbeg + Cfg::EPI_COLS; c0 += 32) {
       float v[32];
       umma::tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, v);
-      if (m < M) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int n = n0 + c0 + j;
-          if (n + 3 < N) {
-            const float o[4] = {v[j], v[j + 1], v[j + 2], v[j + 3]};
-            ep.template store<4>(z, m, n, o);
-          } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (n + q < N) {
-                const float o[1] = {v[j + q]};
-                ep.template store<1>(z, m, n + q, o);
-              }
-          }
-        }
-      }
+      epilogue_store_32x32(ep, stg, lane, z, row0, n0 + c0, M, N, v);
     }
     umma::tc_fence_before();
   } else {
@@ -524,6 +548,7 @@ gemm_umma_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, int
 template <int BN, class BL>
 __global__ void __launch_bounds__(256) retile_b_kernel(const BL bl, int N, int K, int ktiles, int ntn,
                                                         uint8_t* __restrict__ image) {
+  pdl_prologue();
   using TB = UmmaTile<BN, BL::kContigK>;
   constexpr int GPT = BN * 8;                         // float4 groups per tile (BN rows x 32 floats)
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -556,8 +581,7 @@ template <int BN, class BL>
 inline int launch_retile_b(cudaStream_t s, const BL& bl, int N, int K, uint8_t* image) {
   const int ntn = cdiv(N, BN), ktiles = cdiv(K, 32);
   const long long groups = (long long)ntn * ktiles * BN * 8;
-  retile_b_kernel<BN, BL><<<(unsigned)cdiv64(groups, 256), 256, 0, s>>>(bl, N, K, ktiles, ntn, image);
-  DRL_CHECK_LAUNCH();
+  DRL_CUDA_CHECK((launch_k(retile_b_kernel<BN, BL>, (unsigned)cdiv64(groups, 256), 256, 0, s, bl, N, K, ktiles, ntn, image)));
   return DRL_OK;
 }
 
@@ -577,8 +601,7 @@ inline int launch_gemm_umma(cudaStream_t s, const AL& al, const BL& bl, const EP
   }
   if (kchunk < 1 || K < 1) { set_error("gemm_umma: empty K range"); return DRL_ERR_INVALID; }
   dim3 grid(cdiv(M, Cfg::BM), cdiv(N, Cfg::BN), zcount);
-  kern<<<grid, Cfg::NT, SM::BYTES, s>>>(al, bl, ep, M, N, K, kchunk, kstep);
-  DRL_CHECK_LAUNCH();
+  DRL_CUDA_CHECK((launch_k(kern, grid, Cfg::NT, SM::BYTES, s, al, bl, ep, M, N, K, kchunk, kstep)));
   return DRL_OK;
 }
 

@@ -35,6 +35,7 @@ template <class Cfg, class AL, class BL, class EP>
 __global__ void __launch_bounds__(Cfg::NT, 1)
 gemm_umma_persist_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, int kchunk, int kstep,
                          int mtiles, int ntn, int total_tiles) {
+  pdl_prologue();
   constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, STAGES = Cfg::STAGES, NPROD = Cfg::NPROD, PW = Cfg::PW;
   constexpr bool AK = AL::kContigK, BKc = BL::kContigK;
   using SM = UmmaSmem<Cfg, AL, BL>;
@@ -280,6 +281,7 @@ gemm_umma_persist_kernel(const AL al, const BL bl, const EP ep, int M, int N, in
   } else {
     // ================= EPILOGUE (warps PW+1 .. PW+4) =================
     const int quarter = warp & 3;            // TMEM lanes 32*quarter .. +31
+    uint8_t* stg = aux + SM::AUX_BYTES + quarter * kEpiStageBytes;   // dedicated staging: the stages stay live here
     PTile p;
     setup(p, blockIdx.x);
     int i = 0;
@@ -287,7 +289,6 @@ gemm_umma_persist_kernel(const AL al, const BL bl, const EP ep, int M, int N, in
       const int buf = i & 1;
       umma::mbar_wait(&acc_full[buf], ((uint32_t)i >> 1) & 1);
       umma::tc_fence_after();
-      const int m = p.m0 + quarter * 32 + lane;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float v[32];
@@ -296,23 +297,7 @@ gemm_umma_persist_kernel(const AL al, const BL bl, const EP ep, int M, int N, in
           umma::tc_fence_before();
           umma::mbar_arrive(&acc_empty[buf]);
         }
-        if (m < M) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const int n = p.n0 + c0 + j;
-            if (n + 3 < N) {
-              const float o[4] = {v[j], v[j + 1], v[j + 2], v[j + 3]};
-              ep.template store<4>(p.z, m, n, o);
-            } else {
-#pragma unroll
-              for (int qq = 0; qq < 4; ++qq)
-                if (n + qq < N) {
-                  const float o[1] = {v[j + qq]};
-                  ep.template store<1>(p.z, m, n + qq, o);
-                }
-            }
-          }
-        }
+        epilogue_store_32x32(ep, stg, lane, p.z, p.m0 + quarter * 32, p.n0 + c0, M, N, v);
       }
       setup(p, p.tile + gridDim.x);
       ++i;
@@ -343,7 +328,7 @@ inline int launch_gemm_umma_persist(cudaStream_t s, const AL& al, const BL& bl, 
   static bool attr_done = false;
   auto kern = gemm_umma_persist_kernel<Cfg, AL, BL, EP>;
   if (!attr_done) {
-    DRL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::BYTES));
+    DRL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::BYTES + 4 * kEpiStageBytes));
     attr_done = true;
   }
   if ((AL::kContigK || BL::kContigK) && (K % 4 != 0 || kchunk % 4 != 0)) {
@@ -355,8 +340,8 @@ inline int launch_gemm_umma_persist(cudaStream_t s, const AL& al, const BL& bl, 
   const long long total = (long long)mtiles * ntn * zcount;
   if (total > 0x7fffffffLL) { set_error("gemm_umma_persist: too many tiles"); return DRL_ERR_INVALID; }
   const int grid = (int)std::min<long long>(total, device_sm_count());
-  kern<<<grid, Cfg::NT, SM::BYTES, s>>>(al, bl, ep, M, N, K, kchunk, kstep, mtiles, ntn, (int)total);
-  DRL_CHECK_LAUNCH();
+  DRL_CUDA_CHECK((launch_k(kern, grid, Cfg::NT, SM::BYTES + 4 * kEpiStageBytes, s, al, bl, ep, M, N, K, kchunk, kstep,
+                           mtiles, ntn, (int)total)));
   return DRL_OK;
 }
 

@@ -82,6 +82,9 @@ struct VtraceOut {       // parity taps, batch-major [B, T-2]
 constexpr int kLstmSplits = 8;   // slabs allocated for the LSTM split-K partial sums (4 or 7 are used)
 
 // math_mode 0 in drl_learner_config resolves to this (1 = FP32 FFMA, 2 = tcgen05 3xTF32)
+#ifndef DRL_DEFAULT_PDL_LEVEL
+#define DRL_DEFAULT_PDL_LEVEL 0   // programmatic dependent launch (common.cuh); see DESIGN.md for the measurements
+#endif
 #ifndef DRL_DEFAULT_MATH_MODE
 #define DRL_DEFAULT_MATH_MODE 2
 #endif

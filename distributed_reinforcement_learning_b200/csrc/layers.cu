@@ -175,12 +175,14 @@ static int fork_to_side(const Streams& st, int i) {
   if (!st.par) return DRL_OK;
   DRL_CUDA_CHECK(cudaEventRecord(st.ev[i], st.main));
   DRL_CUDA_CHECK(cudaStreamWaitEvent(st.side, st.ev[i], 0));
+  pdl_break(st.side);   // the next side-stream kernel depends on a kernel of another stream: full dependency
   return DRL_OK;
 }
 static int join_from_side(const Streams& st, int i) {
   if (!st.par) return DRL_OK;
   DRL_CUDA_CHECK(cudaEventRecord(st.ev[i], st.side));
   DRL_CUDA_CHECK(cudaStreamWaitEvent(st.main, st.ev[i], 0));
+  pdl_break(st.main);
   return DRL_OK;
 }
 
@@ -262,6 +264,7 @@ int net_forward(const Streams& st, const ParamLayout& pl, const float* P, const 
 
 int net_backward(const Streams& st, const ParamLayout& pl, const float* P, const WeightImages& wi, float* G,
                  const Inputs& in, const Acts& act, const Bwd& bw, int B, int T, int mode) {
+  PdlRegionOff pdl_region;   // DRL_B200_PDL=2: no early launches while the side stream competes for the same SMs
   cudaStream_t s = st.main;
   const cudaStream_t side = st.par ? st.side : st.main;
   const int M = B * T;

@@ -4,7 +4,10 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "kernels.h"
@@ -20,6 +23,23 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
+// programmatic-dependent-launch bookkeeping (common.cuh): per thread, per stream
+bool& pdl_chain_ok(cudaStream_t s) {
+  static thread_local std::unordered_map<cudaStream_t, bool> chain;
+  return chain[s];
+}
+int pdl_level() {
+  static const int level = [] {
+    const char* e = getenv("DRL_B200_PDL");
+    return e ? atoi(e) : DRL_DEFAULT_PDL_LEVEL;
+  }();
+  return level;
+}
+bool& pdl_region_on() {
+  static thread_local bool on = true;
+  return on;
+}
+
 // ---- per-kernel profiler -------------------------------------------------------------------
 struct Profiler {
   bool on = false;
@@ -32,6 +52,7 @@ void prof_mark(cudaStream_t s, const char* name) {
   cudaEvent_t e = nullptr;
   if (cudaEventCreate(&e) != cudaSuccess) return;
   cudaEventRecord(e, s);
+  pdl_break(s);
   g_prof.ev.push_back(e);
   g_prof.names.push_back(name);
 }
@@ -77,6 +98,7 @@ struct drl_learner {
   // CUDA graphs (one per slot) for forward+backward and for apply
   std::vector<cudaGraphExec_t> graph_fb;
   cudaGraphExec_t graph_apply = nullptr;
+  std::vector<cudaGraphExec_t> graph_step;   // forward+backward+apply in one graph (single-GPU step, no all-reduce)
 };
 
 namespace {
@@ -134,6 +156,8 @@ Streams streams_of(const drl_learner* h) {
 // retile = true: (re)build the weight images first.  A training step always does (the parameters changed in the
 // previous apply); the forward-only entry points only when the images are stale.
 int enqueue_forward(drl_learner* h, const Inputs& in, int B, int T, bool retile) {
+  pdl_break(h->compute);   // whatever precedes (event waits, copies) is not a pdl-aware kernel
+  pdl_break(h->side);
   return net_forward(streams_of(h), h->pl, h->params, h->wimg, in, h->act, B, T, h->mode, retile);
 }
 
@@ -149,6 +173,7 @@ int enqueue_forward_backward(drl_learner* h, int slot) {
 }
 
 int enqueue_apply(drl_learner* h) {
+  pdl_break(h->compute);
   prof_mark(h->compute, "optimizer(norm+rmsprop)");
   DRL_TRY(optimizer_apply(h->compute, h->opt));
   prof_mark(h->compute, "end");
@@ -199,6 +224,37 @@ int run_apply(drl_learner* h) {
   } else {
     DRL_TRY(enqueue_apply(h));
   }
+  DRL_CUDA_CHECK(cudaEventRecord(h->ev_stop, h->compute));
+  DRL_CUDA_CHECK(cudaEventRecord(h->ev_done, h->compute));
+  h->pending = true;
+  h->images_stale = true;
+  return DRL_OK;
+}
+
+// Single-GPU step: nothing runs between the backward pass and the update, so both go into ONE graph per slot.
+int run_step(drl_learner* h, int slot) {
+  if (!h->cfg.use_cuda_graph) {
+    DRL_TRY(run_forward_backward(h, slot));
+    return run_apply(h);
+  }
+  Slot& sl = h->slots[slot];
+  if (!sl.has_data) { set_error("slot %d has not been staged", slot); return DRL_ERR_STATE; }
+  DRL_CUDA_CHECK(cudaStreamWaitEvent(h->compute, sl.staged, 0));
+  DRL_CUDA_CHECK(cudaEventRecord(h->ev_start, h->compute));
+  if (!h->graph_step[slot]) {
+    DRL_TRY(enqueue_forward_backward(h, slot));   // eager pass: per-kernel attributes are set outside of capture
+    cudaGraph_t g = nullptr;
+    DRL_CUDA_CHECK(cudaStreamBeginCapture(h->compute, cudaStreamCaptureModeThreadLocal));
+    int r = enqueue_forward_backward(h, slot);
+    if (r == DRL_OK) r = enqueue_apply(h);
+    cudaError_t e = cudaStreamEndCapture(h->compute, &g);
+    if (r != DRL_OK) { if (g) cudaGraphDestroy(g); return r; }
+    if (e != cudaSuccess) { set_error("graph capture failed: %s", cudaGetErrorString(e)); return DRL_ERR_CUDA; }
+    DRL_CUDA_CHECK(cudaGraphInstantiate(&h->graph_step[slot], g, 0));
+    cudaGraphDestroy(g);
+  }
+  DRL_CUDA_CHECK(cudaGraphLaunch(h->graph_step[slot], h->compute));
+  DRL_CUDA_CHECK(cudaEventRecord(sl.consumed, h->compute));
   DRL_CUDA_CHECK(cudaEventRecord(h->ev_stop, h->compute));
   DRL_CUDA_CHECK(cudaEventRecord(h->ev_done, h->compute));
   h->pending = true;
@@ -326,6 +382,7 @@ int drl_learner_create(const drl_learner_config* cfg, drl_learner** out) {
     const size_t BT = (size_t)h->B * h->T;
     h->slots.resize(h->cfg.num_slots);
     h->graph_fb.assign(h->cfg.num_slots, nullptr);
+    h->graph_step.assign(h->cfg.num_slots, nullptr);
     for (Slot& s : h->slots) {
       size_t off = 0;
       const size_t o_frames = off; off = align_up(off + BT * Geo::FRAME, 256);
@@ -366,6 +423,7 @@ int drl_learner_destroy(drl_learner* h) {
   cudaSetDevice(h->cfg.device);
   cudaDeviceSynchronize();
   for (auto g : h->graph_fb) if (g) cudaGraphExecDestroy(g);
+  for (auto g : h->graph_step) if (g) cudaGraphExecDestroy(g);
   if (h->graph_apply) cudaGraphExecDestroy(h->graph_apply);
   for (Slot& s : h->slots) {
     if (s.staged) cudaEventDestroy(s.staged);
@@ -494,8 +552,10 @@ int drl_learner_stream(drl_learner* h, void** stream) {
 }
 
 int drl_learner_step_async(drl_learner* h, int32_t slot) {
-  DRL_TRY(drl_learner_forward_backward(h, slot));
-  return run_apply(h);
+  DRL_TRY(check_handle(h));
+  if (slot < 0 || slot >= (int)h->slots.size()) { set_error("slot %d out of range", slot); return DRL_ERR_INVALID; }
+  DRL_TRY(set_device(h));
+  return run_step(h, slot);
 }
 
 int drl_learner_wait(drl_learner* h, drl_step_out* out) {

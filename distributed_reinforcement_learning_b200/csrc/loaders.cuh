@@ -12,8 +12,14 @@ namespace drl {
 __device__ __forceinline__ float4 u8x4_to_f4(uchar4 u) {
   return make_float4((float)u.x, (float)u.y, (float)u.z, (float)u.w);
 }
+// 4 bytes -> 4 floats without the XU-pipe I2F: PRMT builds the bit pattern of 2^23 + b (0x4B0000bb), one FADD removes
+// the 2^23 (exact for b in [0, 255]).  ncu showed the XU pipe ~29 % busy with I2F.U8 in the conv1 kernels.
 __device__ __forceinline__ float4 u32_bytes_to_f4(uint32_t w) {
-  return make_float4((float)(w & 0xffu), (float)((w >> 8) & 0xffu), (float)((w >> 16) & 0xffu), (float)(w >> 24));
+  const float m = 8388608.0f;
+  return make_float4(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650)) - m,
+                     __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7651)) - m,
+                     __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7652)) - m,
+                     __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7653)) - m);
 }
 // 16 frame bytes (one 128-bit load) -> 16 floats
 __device__ __forceinline__ void unpack_u8x16(const uint4& u, float4 (&f)[4]) {

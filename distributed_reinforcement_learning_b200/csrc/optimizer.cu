@@ -12,6 +12,7 @@
 namespace drl {
 
 __global__ void __launch_bounds__(256) sqnorm_partial_kernel(OptState o) {
+  pdl_prologue();
   __shared__ float red[8];
   const int64_t n4 = o.n / 4;
   const float4* g4 = reinterpret_cast<const float4*>(o.grads);
@@ -41,6 +42,7 @@ __global__ void __launch_bounds__(256) sqnorm_partial_kernel(OptState o) {
 }
 
 __global__ void __launch_bounds__(256) rmsprop_apply_kernel(OptState o) {
+  pdl_prologue();
   __shared__ float red[8];
   __shared__ float s_scale;
   float acc = 0.f;
@@ -83,10 +85,8 @@ __global__ void __launch_bounds__(256) rmsprop_apply_kernel(OptState o) {
 }
 
 int optimizer_apply(cudaStream_t s, const OptState& o) {
-  sqnorm_partial_kernel<<<o.nblk, 256, 0, s>>>(o);
-  DRL_CHECK_LAUNCH();
-  rmsprop_apply_kernel<<<o.nblk, 256, 0, s>>>(o);
-  DRL_CHECK_LAUNCH();
+  DRL_CUDA_CHECK((launch_k(sqnorm_partial_kernel, o.nblk, 256, 0, s, o)));
+  DRL_CUDA_CHECK((launch_k(rmsprop_apply_kernel, o.nblk, 256, 0, s, o)));
   return DRL_OK;
 }
 

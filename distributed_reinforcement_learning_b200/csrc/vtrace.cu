@@ -37,6 +37,7 @@ __device__ __forceinline__ float clip_reward(float r, int mode) {
 __global__ void __launch_bounds__(128) vtrace_losses_kernel(
     VtraceCfg cfg, const float* __restrict__ policy, const float* __restrict__ value, Inputs in, VtraceOut out,
     float* __restrict__ dlogits, float* __restrict__ dv, int B, int T, int A) {
+  pdl_prologue();
   __shared__ float red[4][3];
   __shared__ bool is_last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -130,8 +131,7 @@ __global__ void __launch_bounds__(128) vtrace_losses_kernel(
 int vtrace_losses(cudaStream_t s, const VtraceCfg& cfg, const float* policy, const float* value, const Inputs& in,
                   const VtraceOut& out, float* dlogits, float* dv, int B, int T, int A) {
   if (T < 3 || T > 32) { set_error("trajectory %d outside [3,32]", T); return DRL_ERR_INVALID; }
-  vtrace_losses_kernel<<<cdiv(B, 4), 128, 0, s>>>(cfg, policy, value, in, out, dlogits, dv, B, T, A);
-  DRL_CHECK_LAUNCH();
+  DRL_CUDA_CHECK((launch_k(vtrace_losses_kernel, cdiv(B, 4), 128, 0, s, cfg, policy, value, in, out, dlogits, dv, B, T, A)));
   return DRL_OK;
 }
 
