@@ -36,7 +36,8 @@ T, A, L, B_PER_GPU = 20, 18, 256, 32
 METRIC = "learner env-frames/sec (T=20,B=32/GPU,84x84x4)"
 MATH_MODES = {1: "FP32 FFMA (CUDA cores)",
               2: "tcgen05 kind::tf32, 3xTF32 split (A_lo*B_hi + A_hi*B_lo + A_hi*B_hi), fp32 TMEM accumulate",
-              3: "tcgen05 kind::tf32 3xTF32, persistent warp-specialised kernels (dedicated epilogue warps)"}
+              3: "tcgen05 kind::tf32 3xTF32, persistent warp-specialised kernels (dedicated epilogue warps)",
+              4: "tcgen05 kind::tf32 3xTF32 with TMA-fed conv2/conv3 forward (tensor loads of value + tf32-remainder planes)"}
 
 
 def synth_batch(B, seed):
@@ -463,7 +464,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="launch kernels directly instead of CUDA graphs")
-    ap.add_argument("--math-mode", type=int, default=2, choices=[1, 2, 3],
+    ap.add_argument("--math-mode", type=int, default=2, choices=[1, 2, 3, 4],
                     help="1 = FP32 FFMA contractions, 2 = tcgen05 3xTF32 tensor-core contractions (default)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     args = ap.parse_args()

@@ -164,12 +164,13 @@ struct UmmaTile {
   __device__ static __forceinline__ int kslice_off(int j) { return KMAJOR ? j * 32 : j * 2 * SBO; }
 };
 
-template <int BN_, int STAGES_, int MINB_ = 1, int PW_ = 4>
+template <int BN_, int STAGES_, int MINB_ = 1, int PW_ = 4, int LW_ = 0>
 struct UmmaCfg {
   static constexpr int BM = 128, BN = BN_, BK = 32, STAGES = STAGES_, MINB = MINB_;
   static constexpr int PW = PW_;            // producer / epilogue warps (4 or 8), warps 0..PW-1
+  static constexpr int LW = LW_;            // 1: warp PW+1 issues the bulk copies of a pre-tiled B (see the kernel)
   static constexpr int NPROD = PW * 32;
-  static constexpr int NT = NPROD + 32;     // + the MMA warp (warp PW)
+  static constexpr int NT = NPROD + 32 + 32 * LW;   // + the MMA warp (warp PW) [+ the B loader warp]
   static constexpr int EPI_COLS = BN / (PW / 4);   // accumulator columns each producer warp drains
   static_assert(PW == 4 || PW == 8, "4 or 8 producer warps");
   static_assert(EPI_COLS % 32 == 0, "epilogue reads 32 columns at a time");
@@ -286,6 +287,10 @@ gemm_umma_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, int
   constexpr int NGA = BM * BK / 4, NGB = BN * BK / 4;       // float4 groups per stage
   constexpr bool A16 = loader_vec16<AL>::value;              // 16-element (one 128-bit load) A groups
   constexpr bool BPT = loader_pretiled<BL>::value;           // B arrives as pre-split stage images via cp.async.bulk
+  // A cp.async.bulk blocks its issuing thread for ~0.24 us whatever its size (tools/microbench/tma_box_bw.cu).  Issued
+  // by producer thread 0 that delay sits in front of its own gathers and so of every stage's full barrier; with
+  // Cfg::LW a dedicated warp (PW+1) issues the copies instead and arrives on the barrier itself.
+  constexpr bool LWB = BPT && Cfg::LW;
   constexpr int GA = (A16 ? NGA / 4 : NGA) / NPROD, GB = BPT ? 1 : NGB / NPROD;   // groups per producer thread
   static_assert((A16 ? NGA / 4 : NGA) % NPROD == 0 && NGB % NPROD == 0, "groups must divide among producers");
   static_assert(!A16 || AEX, "16-wide raw loads are only used for exact (uint8) operands");
@@ -311,7 +316,7 @@ gemm_umma_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, int
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      umma::mbar_init(&full[s], NPROD);
+      umma::mbar_init(&full[s], NPROD + (LWB ? 1 : 0));
       umma::mbar_init(&empty[s], 1);
     }
     umma::mbar_init(acc_full, 1);
@@ -403,7 +408,7 @@ gemm_umma_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, int
       const uint32_t ph = (t / STAGES) & 1;
       umma::mbar_wait(&empty[s], ph ^ 1);
       uint8_t* st = smem + s * SM::STAGE_BYTES;
-      if constexpr (BPT) {
+      if constexpr (BPT && !LWB) {
         if (tid == 0) {   // one bulk copy brings [B_hi | B_lo] of this (n-tile, k-tile); bytes complete on full[s]
           const int kt = (k0 + t * BK) / BK;
           umma::mbar_expect_tx(&full[s], 2 * SM::B_BYTES);
@@ -502,8 +507,24 @@ gemm_umma_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, int
       epilogue_store_32x32(ep, stg, lane, z, row0, n0 + c0, M, N, v);
     }
     umma::tc_fence_before();
+  } else if (warp > Cfg::PW) {
+    // ================= B LOADER (warp PW+1, Cfg::LW) =================
+    if constexpr (LWB) {
+      if (lane == 0) {
+        for (int t = 0; t < ntiles; ++t) {
+          const int s = t % STAGES;
+          umma::mbar_wait(&empty[s], ((t / STAGES) & 1) ^ 1);
+          const int kt = (k0 + t * BK) / BK;
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(umma::smem_u32(&full[s])),
+                       "r"(2 * SM::B_BYTES) : "memory");
+          umma::bulk_g2s(smem + s * SM::STAGE_BYTES + OFF_BHI,
+                         bl.image + ((size_t)blockIdx.y * bl.ktiles + kt) * (size_t)(2 * SM::B_BYTES), 2 * SM::B_BYTES,
+                         &full[s]);
+        }
+      }
+    }
   } else {
-    // ================= MMA ISSUER (warp 4) =================
+    // ================= MMA ISSUER (warp PW) =================
     constexpr uint32_t idesc = umma::make_idesc(BN, !AK, !BKc);
     for (int t = 0; t < ntiles; ++t) {
       const int s = t % STAGES;

@@ -37,7 +37,9 @@ struct Inputs {          // one device staging slot, caller's batch-major layout
 
 struct Acts {            // forward activations, time-major rows m = t*B + b, M = B*T rows
   float* a1;             // [M,20,20,32]
+  float* a1_lo;          // tf32 remainder plane of a1 (same shape), allocated right behind a1: TMA operand of conv2
   float* a2;             // [M,9,9,64]
+  float* a2_lo;          // same for a2 (conv3)
   float* a3;             // [M,3136]
   float* e1;             // [A,256]  relu(emb1)
   float* table;          // [A,256]  action-embedding table

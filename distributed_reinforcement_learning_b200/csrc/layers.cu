@@ -8,6 +8,7 @@
 
 #include "gemm_simt.cuh"
 #include "gemm_umma.cuh"
+#include "gemm_tma.cuh"
 #include "gemm_umma_persist.cuh"
 #include "kernels.h"
 #include "loaders.cuh"
@@ -46,6 +47,13 @@ void ParamLayout::init(int num_action) {
 using Conv1A = ConvFwdA<uint8_t, 84, 84, 4, 20, 20, 8, 4, true>;
 using Conv2A = ConvFwdA<float, 20, 20, 32, 9, 9, 4, 2, false>;
 using Conv3A = ConvFwdA<float, 9, 9, 64, 7, 7, 3, 1, false>;
+// math mode 4: TMA-fed forward of conv2 / conv3 (gemm_tma.cuh): tiles of 1 image (81 rows) / 2 images (98 rows), 4 stages.
+// Correct and tested, but measured SLOWER than the software producers on this network (conv2 59 vs 46 us, conv3 41 vs
+// 33 us at B=32, T=20): with 32/64 input channels a K tile is one filter tap, so every activation byte is fetched
+// 4x (conv2) / 9x (conv3) from L2 for each of the two planes plus a 16 KB weight tile per tap and image -- 2.3x the
+// L2->SM bytes of the LDG path, which reads raw fp32 once per tap and splits in registers.
+using Conv2Tma = ConvTmaCfg<32, 20, 9, 4, 2, 1, 4>;
+using Conv3Tma = ConvTmaCfg<64, 9, 7, 3, 1, 2, 4>;
 using Conv1WA = ConvWgradA<uint8_t, 84, 84, 4, 20, 20, 8, 4, true>;
 using Conv2WA = ConvWgradA<float, 20, 20, 32, 9, 9, 4, 2, false>;
 using Conv3WA = ConvWgradA<float, 9, 9, 64, 7, 7, 3, 1, false>;
@@ -60,6 +68,10 @@ using U32 = UmmaCfg<32, 2, 3>;   // 24 KB / stage (A exact: conv1 only), 3 CTAs 
 using U64 = UmmaCfg<64, 2, 2>;   // 48 KB / stage, 2 CTAs per SM
 using U128 = UmmaCfg<128, 3, 1, 8>;   // 64 KB / stage, 1 CTA per SM, 8 producer warps
 using U256 = UmmaCfg<256, 2, 1, 8>;   // 96 KB / stage, 1 CTA per SM, 8 producer warps
+// the same with a B-loader warp, for GEMMs whose B operand is a pre-tiled weight image
+using U64L = UmmaCfg<64, 2, 2, 4, 1>;
+using U128L = UmmaCfg<128, 3, 1, 8, 1>;
+using U256L = UmmaCfg<256, 2, 1, 8, 1>;
 
 // math mode 3 (experimental): the persistent, fully warp-specialised variant of each tensor-core configuration
 template <class U> struct PersistOf;
@@ -67,6 +79,9 @@ template <> struct PersistOf<U32> { using type = UmmaPCfg<32, 5, 8>; };
 template <> struct PersistOf<U64> { using type = UmmaPCfg<64, 4, 8>; };
 template <> struct PersistOf<U128> { using type = UmmaPCfg<128, 3, 8>; };
 template <> struct PersistOf<U256> { using type = UmmaPCfg<256, 2, 8>; };
+template <> struct PersistOf<U64L> { using type = UmmaPCfg<64, 4, 8>; };
+template <> struct PersistOf<U128L> { using type = UmmaPCfg<128, 3, 8>; };
+template <> struct PersistOf<U256L> { using type = UmmaPCfg<256, 2, 8>; };
 
 static int g_fwd_launches = 0, g_bwd_launches = 0;
 int forward_launch_count() { return g_fwd_launches; }
@@ -191,16 +206,25 @@ int net_forward(const Streams& st, const ParamLayout& pl, const float* P, const 
   const int M = B * T;
   const RowMap map{B, T};
   int n = 0, nsplit = 4;
+  const bool tma = mode == 4;
+  if (mode == 4) mode = 2;
   cudaStream_t s = st.main;
   const cudaStream_t side = st.par ? st.side : st.main;
   // action embedding table (:12-16): only A distinct inputs exist; depends on parameters only -> side stream
   DRL_TRY(fork_to_side(st, 0));
   s = side;
+  // weight images of this step's parameters, all on the side stream: the conv2/conv3 forward ones first (main waits
+  // for them behind conv1), the LSTM / dgrad ones behind the embedding table (joined before lstm_fwd)
+  if (retile && mode >= 2) {
+    prof_mark(s, "weight_retile");
+    DRL_TRY((launch_retile_b<64>(s, PlainB{P + pl.conv2_w, 64, 0}, 64, 512, wi.img[1])));
+    DRL_TRY((launch_retile_b<64>(s, PlainB{P + pl.conv3_w, 64, 0}, 64, 576, wi.img[2])));
+    n += 2;
+    if (st.par) DRL_CUDA_CHECK(cudaEventRecord(st.ev[7], side));
+  }
   KERNEL("emb_fwd",
          emb_forward(s, P + pl.emb1_w, P + pl.emb1_b, P + pl.emb2_w, P + pl.emb2_b, act.e1, act.table, pl.A), 1);
   s = st.main;
-  // weight images of this step's parameters: the conv-forward ones on the main stream (needed at once), the LSTM /
-  // dgrad ones behind the embedding table on the side stream, hidden under the conv forward (joined before lstm_fwd)
   if (retile && mode >= 2) {
     DRL_TRY(net_retile(st.main, side, pl, P, wi));
     n += 4;
@@ -209,22 +233,34 @@ int net_forward(const Streams& st, const ParamLayout& pl, const float* P, const 
   {
     Conv1A al{in.frames, map};
     PlainB bl{P + pl.conv1_w, 32, 0};
-    EpConv1 ep{act.a1, 32, P + pl.conv1_b};
+    EpConv1 ep{act.a1, 32, P + pl.conv1_b, tma ? act.a1_lo : nullptr};
     GEMM("conv1_fwd", CfgN32, U32, al, bl, ep, M * 400, 32, 256, 1, 256, 0);
   }
+  if (retile && mode >= 2 && st.par) {
+    DRL_CUDA_CHECK(cudaStreamWaitEvent(st.main, st.ev[7], 0));
+    pdl_break(st.main);
+  }
   // conv2 -> a2 [M,9,9,64]   (:7)
-  {
+  if (tma) {
+    EpBiasAct<true, true> ep{act.a2, 64, 0, P + pl.conv2_b, 0, 1.0f, act.a2_lo};
+    KERNEL("conv2_fwd", (launch_conv_fwd_tma<Conv2Tma>(s, act.a1, (size_t)(act.a1_lo - act.a1), M, wi.img[1], ep)), 1);
+  } else {
     Conv2A al{act.a1, map};
     PlainB bl{P + pl.conv2_w, 64, 0};
+    PretiledB<PlainB> blp{wi.img[1], 512 / 32};
     EpBiasAct<true, true> ep{act.a2, 64, 0, P + pl.conv2_b, 0, 1.0f};
-    GEMM("conv2_fwd", CfgBig, U64, al, bl, ep, M * 81, 64, 512, 1, 512, 0);
+    GEMM_W("conv2_fwd", CfgBig, U64L, al, bl, blp, ep, M * 81, 64, 512, 1, 512, 0);
   }
   // conv3 -> a3 [M,7,7,64] = flatten HWC [M,3136]   (:8-10)
-  {
+  if (tma) {
+    EpBiasAct<true, true> ep{act.a3, 64, 0, P + pl.conv3_b, 0, 1.0f};
+    KERNEL("conv3_fwd", (launch_conv_fwd_tma<Conv3Tma>(s, act.a2, (size_t)(act.a2_lo - act.a2), M, wi.img[2], ep)), 1);
+  } else {
     Conv3A al{act.a2, map};
     PlainB bl{P + pl.conv3_w, 64, 0};
+    PretiledB<PlainB> blp{wi.img[2], 576 / 32};
     EpBiasAct<true, true> ep{act.a3, 64, 0, P + pl.conv3_b, 0, 1.0f};
-    GEMM("conv3_fwd", CfgBig, U64, al, bl, ep, M * 49, 64, 576, 1, 576, 0);
+    GEMM_W("conv3_fwd", CfgBig, U64L, al, bl, blp, ep, M * 49, 64, 576, 1, 576, 0);
   }
   DRL_TRY(join_from_side(st, 1));
   // LSTM pre-activation z = [a3 | emb | h0] W  (split-K partial sums; bias added in the gate kernel) (:18-25)
@@ -236,7 +272,7 @@ int net_forward(const Streams& st, const ParamLayout& pl, const float* P, const 
     nsplit = (mode >= 2) ? 7 : 4;
     const int kchunk = (mode >= 2) ? 544 : Geo::XK / 4;
     PretiledB<PlainB> blp{wi.img[3], Geo::XK / 32};
-    GEMM_W("lstm_fwd", CfgMid, U256, al, bl, blp, ep, M, Geo::G4, Geo::XK, nsplit, kchunk, kchunk);
+    GEMM_W("lstm_fwd", CfgMid, U256L, al, bl, blp, ep, M, Geo::G4, Geo::XK, nsplit, kchunk, kchunk);
   }
   KERNEL("lstm_gates_fwd",
          lstm_gates_forward(s, act.zpart, nsplit, P + pl.lstm_b, in.c0, act.gates, act.c1, act.tc1, act.h1, M, B,
@@ -265,6 +301,7 @@ int net_forward(const Streams& st, const ParamLayout& pl, const float* P, const 
 int net_backward(const Streams& st, const ParamLayout& pl, const float* P, const WeightImages& wi, float* G,
                  const Inputs& in, const Acts& act, const Bwd& bw, int B, int T, int mode) {
   PdlRegionOff pdl_region;   // DRL_B200_PDL=2: no early launches while the side stream competes for the same SMs
+  if (mode == 4) mode = 2;
   cudaStream_t s = st.main;
   const cudaStream_t side = st.par ? st.side : st.main;
   const int M = B * T;
@@ -337,7 +374,7 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, const
     PlainBT bl{P + pl.lstm_w, Geo::G4, 0};
     EpLstmDx ep{bw.da3, act.a3, bw.du};
     PretiledB<PlainBT> blp{wi.img[4], Geo::G4 / 32};
-    GEMM_W("lstm_dgrad", CfgMid, U128, al, bl, blp, ep, Mb, Geo::FLAT + Geo::EMB, Geo::G4, 1, Geo::G4, 0);
+    GEMM_W("lstm_dgrad", CfgMid, U128L, al, bl, blp, ep, Mb, Geo::FLAT + Geo::EMB, Geo::G4, 1, Geo::G4, 0);
   }
   // ---- action embedding + conv3 weight gradient (side) -------------------------------------
   DRL_TRY(fork_to_side(st, 4));

@@ -291,7 +291,11 @@ int drl_learner_create(const drl_learner_config* cfg, drl_learner** out) {
     set_error("reward_clipping must be DRL_REWARD_ABS_ONE or DRL_REWARD_SOFT_ASYMMETRIC");   // utils.py:45
     return DRL_ERR_INVALID;
   }
-  if (cfg->math_mode < 0 || cfg->math_mode > 3) { set_error("math_mode must be 0 (default), 1 (FP32 FFMA), 2 (tcgen05 3xTF32) or 3 (tcgen05 3xTF32, persistent kernels)"); return DRL_ERR_INVALID; }
+  if (cfg->math_mode < 0 || cfg->math_mode > 4) {
+    set_error("math_mode must be 0 (default), 1 (FP32 FFMA), 2 (tcgen05 3xTF32), 3 (same, persistent kernels) or "
+              "4 (same as 2 with TMA-fed conv2/conv3 forward)");
+    return DRL_ERR_INVALID;
+  }
   if (drl_device_count() <= cfg->device) { set_error("CUDA device %d not available (no CPU fallback)", cfg->device); return DRL_ERR_CUDA; }
 
   drl_learner* h = new drl_learner();
@@ -319,8 +323,11 @@ int drl_learner_create(const drl_learner_config* cfg, drl_learner** out) {
       DRL_CUDA_CHECK(cudaMemcpy(h->ms, ones.data(), NP * sizeof(float), cudaMemcpyHostToDevice));
     }
     Acts& a = h->act;
-    DRL_TRY(dev_alloc(h, &a.a1, M * 400 * 32));
-    DRL_TRY(dev_alloc(h, &a.a2, M * 81 * 64));
+    const size_t planes = (h->mode == 4) ? 2 : 1;      // math mode 4: [value plane | tf32 remainder plane]
+    DRL_TRY(dev_alloc(h, &a.a1, planes * M * 400 * 32));
+    a.a1_lo = (planes == 2) ? a.a1 + M * 400 * 32 : nullptr;
+    DRL_TRY(dev_alloc(h, &a.a2, planes * M * 81 * 64));
+    a.a2_lo = (planes == 2) ? a.a2 + M * 81 * 64 : nullptr;
     DRL_TRY(dev_alloc(h, &a.a3, M * Geo::FLAT));
     DRL_TRY(dev_alloc(h, &a.e1, A * Geo::EMB));
     DRL_TRY(dev_alloc(h, &a.table, A * Geo::EMB));
