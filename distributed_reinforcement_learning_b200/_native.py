@@ -80,6 +80,7 @@ def _load():
         "drl_learner_act": (C.c_int, [vp, i32] + [vp] * 7),
         "drl_learner_profile_step": (C.c_int, [vp, i32, C.c_char_p, i64, vp, i32, C.POINTER(i32)]),
         "drl_debug_gemm": (C.c_int, [i32] * 8 + [vp, vp, vp]),
+        "drl_debug_trace": (C.c_int, [vp]),
         "drl_learner_last_step_ms": (C.c_int, [vp, C.POINTER(f32)]),
         "drl_learner_launches_per_step": (C.c_int, [vp, C.POINTER(i32)]),
         "drl_vtrace_from_importance_weights": (C.c_int, [vp] * 5 + [i32, i32, f32, vp, vp]),

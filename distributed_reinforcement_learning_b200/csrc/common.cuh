@@ -51,10 +51,29 @@ static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // launch_k(), which sets the programmatic-stream-serialization attribute only when the previous operation on the
 // stream was another such kernel (pdl_break() marks event waits, copies and API entry points).  Under stream
 // capture the attribute becomes a programmatic edge of the CUDA graph.  DRL_B200_PDL=0 turns the attribute off.
+// Optional start-time trace (drl_debug_trace): when armed, CTA (0,0,0) of every kernel appends
+// {globaltimer ns, grid size << 32 | block size} to a device buffer, which gives the true kernel timeline inside a
+// CUDA-graph replay (both streams), something CUDA events cannot do without serialising the graph.  The pointer is a
+// per-translation-unit device global (no relocatable device code); every TU registers a setter at load time.
+static __device__ unsigned long long* g_trace_tu = nullptr;
 __device__ __forceinline__ void pdl_prologue() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  unsigned long long* tr = g_trace_tu;
+  if (tr != nullptr && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const unsigned long long i = atomicAdd(tr, 1ULL);
+    if (i < 4000ULL) {
+      tr[1 + 2 * i] = t;
+      tr[2 + 2 * i] = ((unsigned long long)(gridDim.x * gridDim.y * gridDim.z) << 32) | (unsigned long long)blockDim.x;
+    }
+  }
 }
+typedef void (*TraceSetter)(unsigned long long*);
+int register_trace_setter(TraceSetter f);            // learner.cu
+static void trace_set_tu(unsigned long long* p) { cudaMemcpyToSymbol(g_trace_tu, &p, sizeof(p)); }
+static const int g_trace_registered = register_trace_setter(&trace_set_tu);
 bool& pdl_chain_ok(cudaStream_t s);   // per calling thread: was the last thing enqueued on s a pdl-aware kernel?
 int pdl_level();                      // DRL_B200_PDL: 0 off, 1 every chained launch, 2 outside the backward pass,
                                       // 3 only launches without dynamic shared memory (the elementwise kernels)

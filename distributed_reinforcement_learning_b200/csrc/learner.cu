@@ -35,6 +35,14 @@ int pdl_level() {
   }();
   return level;
 }
+static std::vector<TraceSetter>& trace_setters() {
+  static std::vector<TraceSetter> v;
+  return v;
+}
+int register_trace_setter(TraceSetter f) {
+  trace_setters().push_back(f);
+  return (int)trace_setters().size();
+}
 bool& pdl_region_on() {
   static thread_local bool on = true;
   return on;
@@ -267,6 +275,16 @@ int run_step(drl_learner* h, int slot) {
 extern "C" {
 
 const char* drl_last_error(void) { return get_error(); }
+
+// debug: arm (dev_buf = device buffer of >= 8001 uint64, word 0 = entry counter) or disarm (NULL) the kernel
+// start-time trace of common.cuh::pdl_prologue
+int drl_debug_trace(void* dev_buf) {
+  if (drl_device_count() < 1) { set_error("CUDA device not available (no CPU fallback)"); return DRL_ERR_CUDA; }
+  DRL_CUDA_CHECK(cudaDeviceSynchronize());
+  for (TraceSetter f : trace_setters()) f(static_cast<unsigned long long*>(dev_buf));
+  DRL_CUDA_CHECK(cudaDeviceSynchronize());
+  return DRL_OK;
+}
 const char* drl_version(void) { return "drl_b200 0.1 (sm_100a; FP32-FFMA gather-GEMM path)"; }
 
 int drl_device_count(void) {

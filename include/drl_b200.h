@@ -156,6 +156,10 @@ int drl_learner_profile_step(drl_learner* h, int32_t slot, char* names, int64_t 
  * C: `splits` slabs of [(M+1), N] floats (split-K partials; row M = column sums of B for N-major B). */
 int drl_debug_gemm(int32_t core, int32_t bn, int32_t a_kmajor, int32_t b_kmajor, int32_t M, int32_t N,
                    int32_t K, int32_t splits, const float* A, const float* B, float* C);
+/* Test aid: arm (dev_buf: device buffer of >= 8001 uint64, word 0 = entry count, zeroed by the caller) or disarm
+ * (NULL) the kernel start-time trace: CTA 0 of every kernel of the step appends {globaltimer ns, grid size << 32 |
+ * block size}.  Gives the true timeline of a CUDA-graph replay across both streams (tools/timeline.py). */
+int drl_debug_trace(void* dev_buf);
 /* Device-time of the last step's compute (CUDA events on the compute stream), milliseconds. */
 int drl_learner_last_step_ms(drl_learner* h, float* ms);
 /* Number of kernel launches one step issues (for bench.py's gpu_launches claim). */

@@ -1,0 +1,61 @@
+"""True kernel timeline of one learner step inside the CUDA-graph replay (both streams).
+
+    python tools/timeline.py [--math-mode 2] [--no-graph]
+
+Arms drl_debug_trace: CTA 0 of every kernel records {globaltimer, grid, block} when it starts (after its
+griddepcontrol.wait).  Prints the start times relative to the first kernel, the gap to the next start on the device
+and the launch geometry, so each kernel can be recognised (conv1_fwd = 2000 CTAs x 160 threads, ...)."""
+import argparse
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from distributed_reinforcement_learning_b200 import _native as N   # noqa: E402
+from distributed_reinforcement_learning_b200.learner import NativeLearner   # noqa: E402
+from bench import synth_batch   # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--math-mode", type=int, default=2)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--steps", type=int, default=3)
+    a = ap.parse_args()
+    B, T = a.batch, 20
+    eng = NativeLearner(batch=B, trajectory=T, num_action=18, use_cuda_graph=not a.no_graph, math_mode=a.math_mode)
+    bt = synth_batch(B, 1)
+    fields = ("state", "reward", "action", "done", "behavior_policy", "previous_action", "initial_h", "initial_c")
+    for s in range(2):
+        eng.stage(s, *[bt[f] for f in fields])
+    for i in range(6):
+        eng.step(i % 2)
+    buf = torch.zeros(8001, dtype=torch.int64, device="cuda")
+    N.check(N.lib.drl_debug_trace(C.c_void_p(buf.data_ptr())))
+    per_step = []
+    for i in range(a.steps):
+        buf.zero_()
+        torch.cuda.synchronize()
+        eng.step(i % 2)
+        torch.cuda.synchronize()
+        h = buf.cpu().numpy()
+        n = int(h[0])
+        rec = sorted((int(h[1 + 2 * j]), int(h[2 + 2 * j])) for j in range(n))
+        per_step.append(rec)
+    N.check(N.lib.drl_debug_trace(C.c_void_p(0)))
+    rec = per_step[-1]
+    t0 = rec[0][0]
+    print("# %d kernels, first start -> last start %.1f us (steps: %s)" % (
+        len(rec), (rec[-1][0] - t0) / 1e3, ", ".join("%.1f" % ((r[-1][0] - r[0][0]) / 1e3) for r in per_step)))
+    print("# start_us  next_start_in_us  grid  block")
+    for j, (t, g) in enumerate(rec):
+        nxt = (rec[j + 1][0] - t) / 1e3 if j + 1 < len(rec) else 0.0
+        print("%9.1f %9.1f %7d %5d" % ((t - t0) / 1e3, nxt, g >> 32, g & 0xffffffff))
+
+
+if __name__ == "__main__":
+    main()
