@@ -404,6 +404,7 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, const
     prof_mark(s, "conv3_dgrad");
     PretiledB<PlainBT> blp{wi.img[5], 2};
     DRL_TRY((launch_gemm_umma_persist<PersistOf<U256>::type>(s, al, blp, ep, Mb * 49, 576, 64, 1, 64, 0)));
+    prof_mark(s, "conv3_col2im");
     DRL_TRY(col2im_conv3(s, bw.dcol, act.a2, bw.da2, Mb));
     n += 2;
   } else {
@@ -432,6 +433,7 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, const
     prof_mark(s, "conv2_dgrad");                      // persistent kernel: 0.079 vs 0.091 ms
     PretiledB<PlainBT> blp{wi.img[6], 2};
     DRL_TRY((launch_gemm_umma_persist<PersistOf<U256>::type>(s, al, blp, ep, Mb * 81, 512, 64, 1, 64, 0)));
+    prof_mark(s, "conv2_col2im");
     DRL_TRY(col2im_conv2(s, bw.dcol, act.a1, bw.da1, Mb));
     n += 2;
   } else {
