@@ -261,11 +261,16 @@ def run_ours(args):
     torch.cuda.set_device(local)
     B, K, W = B_PER_GPU, args.steps, max(args.warmup, 3)
     M, Mb = B * T, B * (T - 2)
-    # forward+backward and clip+RMSProp are two separate CUDA graphs; at N > 1 the NCCL all-reduce runs between them
+    # N = 1: the whole step is one CUDA graph.  N > 1, --collective peer (default): still one graph, the gradient
+    # exchange runs as kernels over NVLink peer memory (csrc/peer.cu); --collective nccl: forward+backward and
+    # clip+RMSProp are two graphs with torch.distributed's NCCL all_reduce of the bucket between them.
     use_graph = not args.no_graph
     eng = NativeLearner(batch=B, trajectory=T, num_action=A, device=local, num_slots=2, use_cuda_graph=use_graph,
                         math_mode=args.math_mode)
     eng.set_params(model.init_params(seed=0))
+    if world > 1 and args.collective == "peer":
+        eng.enable_peer_exchange()
+    eng._no_collective = world > 1 and args.collective == "none"
     ext = torch.cuda.ExternalStream(eng.stream_ptr(), device="cuda:%d" % local)
 
     # host data: 3 distinct batches in a pinned trajectory ring (the FIFOQueue replacement)
@@ -378,6 +383,8 @@ def run_ours(args):
             line_extra["roofline_vtrace"] = {"error": str(ex)}
         if args.cpu_baseline and world == 1:      # rank 0 at N=1 only
             line_extra["cpu_baseline"] = cpu_reference(3, 1)
+    if world > 1:
+        dist.barrier()           # peers' buffers stay mapped until everybody is done
     eng.close()
     if rank == 0:
         fps = world * B * T / (ms_dev / K * 1e-3)
@@ -388,6 +395,11 @@ def run_ours(args):
                 "config": {"workload": "IMPALA learner step (BASELINE configs[1]): B=32 trajectories/GPU, T=20, "
                                        "84x84x4 uint8, A=18, LSTM 256; glorot random-init parameters",
                            "global_batch": world * B, "trajectory": T, "parallelism": "dp%d" % world,
+                           "collective": (None if world == 1 else
+                                          "fused reduce-scatter/all-gather kernels over NVLink peer memory (CUDA IPC) "
+                                          "inside the step graph" if args.collective == "peer" else
+                                          "NCCL all_reduce(SUM) of the 16.6 MB bucket between two graphs"
+                                          if args.collective == "nccl" else "NONE (diagnostic, invalid)"),
                            "l2": "inputs+activations+params ~230 MB/step > 126 MB L2; two staging slots alternate",
                            "cuda_graph": bool(use_graph), "math_mode": MATH_MODES[args.math_mode]},
                 "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,
@@ -470,6 +482,9 @@ def main():
     ap.add_argument("--math-mode", type=int, default=2, choices=[1, 2, 3, 4],
                     help="1 = FP32 FFMA contractions, 2 = tcgen05 3xTF32 tensor-core contractions (default)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--collective", choices=["peer", "nccl", "none"], default="peer",
+                    help="N > 1: fused peer-memory gradient exchange (default) or NCCL all_reduce; 'none' = no "
+                         "exchange at all (diagnostic: N independent replicas, NOT a valid data-parallel step)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

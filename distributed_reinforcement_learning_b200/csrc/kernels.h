@@ -155,7 +155,11 @@ int vtrace_losses(cudaStream_t s, const VtraceCfg& cfg, const float* policy, con
 struct OptState {
   float* params; float* ms; float* grads;   // padded flat vectors
   int64_t n;                                 // padded_total (multiple of 4)
-  float* norm_partials; int nblk;
+  float* norm_partials; int nblk;            // partial sums of squares; grid size of the two optimizer kernels
+  int npart;                                 // how many partials the update kernel sums (nblk, or world * nblk_r)
+  // peer exchange (peer.cu): the update kernel first waits for the peers' barrier-1 flags (null: single replica)
+  const uint32_t* wait_flags; const uint32_t* wait_epoch; int wait_world; uint32_t* wait_err;
+  int wait_parts;                            // exchange instances to wait for
   long long* step;                           // device global_step
   float* lr_cur;                             // device scalar
   float* out;                                // device [8]: pi, baseline, entropy, lr, grad_norm, total, step_lo, step_hi
@@ -164,5 +168,25 @@ struct OptState {
   float clip_norm, baseline_coef, entropy_coef;
 };
 int optimizer_apply(cudaStream_t s, const OptState& o);
+int optimizer_update_only(cudaStream_t s, const OptState& o);   // clip + RMSProp from already reduced partials
+
+// ---- peer.cu: gradient exchange over NVLink peer memory (CUDA IPC), fused with the norm ------------------------
+constexpr int kMaxPeers = 16;
+constexpr int kPeerParts = 1;      // exchange instances per step (the kernel takes a sub-range: see DESIGN.md section 5)
+struct PeerTable {                 // device pointers into every rank's buffers (index = rank; own entries are local)
+  float* bucket[kMaxPeers];        // [padded grads | 4 loss sums]
+  float* reduced[kMaxPeers];       // same shape: the summed bucket, delivered by the owners of the slices
+  float* partials[kMaxPeers];      // [world * nblk_r] partial squared norms
+  uint32_t* flags[kMaxPeers];      // [2 * kPeerParts][kMaxPeers] barrier epochs (phase = 2 * part + {ready, delivered})
+  uint32_t* epoch[kMaxPeers];      // per part 4 words: epochs completed (x2), CTA ticket counter (own entry only)
+  uint32_t* err[kMaxPeers];        // barrier time-out report (only the own entry is used)
+};
+struct PeerPlan {
+  PeerTable t;
+  OptState o;                      // the update's state (lr / step live here)
+  int rank, world, nblk;
+};
+// one exchange instance over float4 range [beg4, end4) of the bucket; do_lr: also lr / global_step (last instance)
+int peer_exchange(cudaStream_t s, const PeerPlan& pp, int part, int64_t beg4, int64_t end4, bool do_lr);
 
 }  // namespace drl

@@ -106,7 +106,15 @@ struct drl_learner {
   // CUDA graphs (one per slot) for forward+backward and for apply
   std::vector<cudaGraphExec_t> graph_fb;
   cudaGraphExec_t graph_apply = nullptr;
-  std::vector<cudaGraphExec_t> graph_step;   // forward+backward+apply in one graph (single-GPU step, no all-reduce)
+  std::vector<cudaGraphExec_t> graph_step;   // forward+backward+[exchange]+apply in one graph
+  // gradient exchange over NVLink peer memory (peer.cu); off until drl_learner_peer_import
+  bool peer_on = false;
+  int peer_nblk = 148 * 4;
+  uint8_t* comm = nullptr;                   // [reduced | partials | flags | epochs | err], own cudaMalloc (IPC-exported)
+  size_t comm_bytes = 0, off_partials = 0, off_flags = 0, off_epoch = 0, off_err = 0;
+  PeerPlan plan{};                           // peer table + the update's OptState on the reduced buffer
+  std::vector<void*> peer_opened;            // bases returned by cudaIpcOpenMemHandle
+  uint32_t* h_peer_err = nullptr;            // pinned copy of the barrier time-out word
 };
 
 namespace {
@@ -180,11 +188,22 @@ int enqueue_forward_backward(drl_learner* h, int slot) {
   return DRL_OK;
 }
 
-int enqueue_apply(drl_learner* h) {
+// local_only: the single-replica update on the local bucket even when the peer exchange is on (profiling on one rank)
+int enqueue_apply(drl_learner* h, bool local_only = false) {
   pdl_break(h->compute);
-  prof_mark(h->compute, "optimizer(norm+rmsprop)");
-  DRL_TRY(optimizer_apply(h->compute, h->opt));
-  prof_mark(h->compute, "end");
+  if (h->peer_on && !local_only) {
+    prof_mark(h->compute, "peer_exchange");
+    DRL_TRY(peer_exchange(h->compute, h->plan, 0, 0, h->pl.padded_total / 4 + 1, true));   // grads + loss sums
+    prof_mark(h->compute, "optimizer(rmsprop)");
+    DRL_TRY(optimizer_update_only(h->compute, h->plan.o));
+    prof_mark(h->compute, "end");
+    DRL_CUDA_CHECK(cudaMemcpyAsync(h->h_peer_err, h->comm + h->off_err, sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                   h->compute));
+  } else {
+    prof_mark(h->compute, "optimizer(norm+rmsprop)");
+    DRL_TRY(optimizer_apply(h->compute, h->opt));
+    prof_mark(h->compute, "end");
+  }
   DRL_CUDA_CHECK(cudaMemcpyAsync(h->h_out, h->d_out, 8 * sizeof(float), cudaMemcpyDeviceToHost, h->compute));
   return DRL_OK;
 }
@@ -399,6 +418,8 @@ int drl_learner_create(const drl_learner_config* cfg, drl_learner** out) {
     OptState& o = h->opt;
     o.params = h->params; o.ms = h->ms; o.grads = h->bucket; o.n = (int64_t)NP;
     o.nblk = 148 * 4;
+    o.npart = o.nblk;
+    o.wait_flags = nullptr; o.wait_epoch = nullptr; o.wait_world = 0; o.wait_err = nullptr; o.wait_parts = 0;
     DRL_TRY(dev_alloc(h, &o.norm_partials, o.nblk));
     o.step = h->d_step; o.lr_cur = h->d_lr; o.out = h->d_out; o.loss_sums = v.loss_sums;
     o.start_lr = cfg->start_learning_rate; o.end_lr = cfg->end_learning_rate; o.learning_frame = cfg->learning_frame;
@@ -454,6 +475,9 @@ int drl_learner_destroy(drl_learner* h) {
     if (s.staged) cudaEventDestroy(s.staged);
     if (s.consumed) cudaEventDestroy(s.consumed);
   }
+  for (void* p : h->peer_opened) cudaIpcCloseMemHandle(p);
+  if (h->comm) cudaFree(h->comm);
+  if (h->h_peer_err) cudaFreeHost(h->h_peer_err);
   for (void* p : h->allocs) cudaFree(p);
   if (h->h_out) cudaFreeHost(h->h_out);
   if (h->h_flat) cudaFreeHost(h->h_flat);
@@ -516,7 +540,7 @@ int drl_learner_get_grads(drl_learner* h, float* host_flat, int64_t n) {
   DRL_TRY(check_handle(h));
   if (!host_flat || n != h->pl.packed_total) { set_error("get_grads: expected %lld floats", (long long)h->pl.packed_total); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
-  return download_flat(h, h->bucket, host_flat);
+  return download_flat(h, h->peer_on ? reinterpret_cast<float*>(h->comm) : h->bucket, host_flat);
 }
 
 int drl_learner_stage(drl_learner* h, int32_t slot, const uint8_t* state, const float* reward, const int32_t* action,
@@ -569,6 +593,79 @@ int drl_learner_apply(drl_learner* h) {
   return run_apply(h);
 }
 
+// ---- gradient exchange over NVLink peer memory (peer.cu) -------------------------------------------------------
+int drl_learner_peer_export(drl_learner* h, void* handles, int64_t bytes) {
+  DRL_TRY(check_handle(h));
+  if (!handles || bytes != 2 * (int64_t)sizeof(cudaIpcMemHandle_t)) { set_error("peer_export: expected a %d-byte buffer", (int)(2 * sizeof(cudaIpcMemHandle_t))); return DRL_ERR_INVALID; }
+  DRL_TRY(set_device(h));
+  if (!h->comm) {
+    const size_t red = align_up((size_t)(h->pl.padded_total + 4) * sizeof(float), 256);
+    h->off_partials = red;
+    h->off_flags = h->off_partials + align_up((size_t)kPeerParts * kMaxPeers * h->peer_nblk * sizeof(float), 256);
+    h->off_epoch = h->off_flags + 2 * kPeerParts * kMaxPeers * sizeof(uint32_t);
+    h->off_err = h->off_epoch + 4 * kPeerParts * sizeof(uint32_t);
+    h->comm_bytes = h->off_err + 256;
+    DRL_CUDA_CHECK(cudaMalloc((void**)&h->comm, h->comm_bytes));
+    DRL_CUDA_CHECK(cudaMemset(h->comm, 0, h->comm_bytes));
+    DRL_CUDA_CHECK(cudaHostAlloc((void**)&h->h_peer_err, sizeof(uint32_t), cudaHostAllocDefault));
+    *h->h_peer_err = 0;
+  }
+  cudaIpcMemHandle_t hd[2];
+  DRL_CUDA_CHECK(cudaIpcGetMemHandle(&hd[0], h->bucket));
+  DRL_CUDA_CHECK(cudaIpcGetMemHandle(&hd[1], h->comm));
+  memcpy(handles, hd, sizeof(hd));
+  return DRL_OK;
+}
+
+int drl_learner_peer_import(drl_learner* h, int32_t rank, int32_t world, const void* all_handles, int64_t bytes) {
+  DRL_TRY(check_handle(h));
+  if (world < 2 || world > kMaxPeers || rank < 0 || rank >= world) { set_error("peer_import: bad rank %d / world %d (max %d)", rank, world, kMaxPeers); return DRL_ERR_INVALID; }
+  if (!all_handles || bytes != (int64_t)world * 2 * (int64_t)sizeof(cudaIpcMemHandle_t)) { set_error("peer_import: expected world x %d bytes", (int)(2 * sizeof(cudaIpcMemHandle_t))); return DRL_ERR_INVALID; }
+  if (!h->comm) { set_error("peer_import before peer_export"); return DRL_ERR_STATE; }
+  if (h->peer_on) { set_error("peer exchange already set up"); return DRL_ERR_STATE; }
+  DRL_TRY(set_device(h));
+  DRL_CUDA_CHECK(cudaDeviceSynchronize());
+  const cudaIpcMemHandle_t* hd = static_cast<const cudaIpcMemHandle_t*>(all_handles);
+  for (int p = 0; p < world; ++p) {
+    float* bucket = h->bucket;
+    uint8_t* comm = h->comm;
+    if (p != rank) {
+      void *b = nullptr, *c = nullptr;
+      DRL_CUDA_CHECK(cudaIpcOpenMemHandle(&b, hd[2 * p], cudaIpcMemLazyEnablePeerAccess));
+      h->peer_opened.push_back(b);
+      DRL_CUDA_CHECK(cudaIpcOpenMemHandle(&c, hd[2 * p + 1], cudaIpcMemLazyEnablePeerAccess));
+      h->peer_opened.push_back(c);
+      bucket = static_cast<float*>(b);
+      comm = static_cast<uint8_t*>(c);
+    }
+    h->plan.t.bucket[p] = bucket;
+    h->plan.t.reduced[p] = reinterpret_cast<float*>(comm);
+    h->plan.t.partials[p] = reinterpret_cast<float*>(comm + h->off_partials);
+    h->plan.t.flags[p] = reinterpret_cast<uint32_t*>(comm + h->off_flags);
+    h->plan.t.epoch[p] = reinterpret_cast<uint32_t*>(comm + h->off_epoch);
+    h->plan.t.err[p] = reinterpret_cast<uint32_t*>(comm + h->off_err);
+  }
+  h->plan.rank = rank;
+  h->plan.world = world;
+  h->plan.nblk = h->peer_nblk;
+  OptState& po = h->plan.o;
+  po = h->opt;
+  po.grads = reinterpret_cast<float*>(h->comm);
+  po.norm_partials = reinterpret_cast<float*>(h->comm + h->off_partials);
+  po.npart = kPeerParts * world * h->peer_nblk;
+  po.loss_sums = reinterpret_cast<float*>(h->comm) + h->pl.padded_total;
+  po.wait_flags = h->plan.t.flags[rank];
+  po.wait_epoch = h->plan.t.epoch[rank];
+  po.wait_world = world;
+  po.wait_err = h->plan.t.err[rank];
+  po.wait_parts = kPeerParts;
+  // graphs captured so far do not contain the exchange
+  for (auto& g : h->graph_step) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+  if (h->graph_apply) { cudaGraphExecDestroy(h->graph_apply); h->graph_apply = nullptr; }
+  h->peer_on = true;
+  return DRL_OK;
+}
+
 int drl_learner_stream(drl_learner* h, void** stream) {
   DRL_TRY(check_handle(h));
   if (!stream) { set_error("null argument"); return DRL_ERR_INVALID; }
@@ -589,6 +686,10 @@ int drl_learner_wait(drl_learner* h, drl_step_out* out) {
   DRL_TRY(set_device(h));
   DRL_CUDA_CHECK(cudaEventSynchronize(h->ev_done));
   h->pending = false;
+  if (h->peer_on && h->h_peer_err && *h->h_peer_err) {
+    set_error("peer exchange: rank %d never reached the barrier (20 s)", (int)*h->h_peer_err - 1);
+    return DRL_ERR_STATE;
+  }
   if (out) {
     out->pi_loss = h->h_out[0];
     out->baseline_loss = h->h_out[1];
@@ -717,7 +818,7 @@ int drl_learner_profile_step(drl_learner* h, int32_t slot, char* names, int64_t 
   const bool par_saved = h->par;
   h->par = false;                       // serial: the event-to-event times are then per kernel
   int rc = enqueue_forward_backward(h, slot);
-  if (rc == DRL_OK) rc = enqueue_apply(h);
+  if (rc == DRL_OK) rc = enqueue_apply(h, /*local_only=*/true);   // one rank may profile alone
   h->par = par_saved;
   g_prof.on = false;
   cudaError_t e = cudaStreamSynchronize(h->compute);

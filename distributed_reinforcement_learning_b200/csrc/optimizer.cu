@@ -8,6 +8,7 @@
 // block re-reduces the partials in a fixed order (deterministic) and applies the update.
 // HBM traffic: read g twice (second time from L2), read+write w and ms: ~5 x 16.6 MB.
 #include "kernels.h"
+#include "peer_sync.cuh"
 
 namespace drl {
 
@@ -45,8 +46,13 @@ __global__ void __launch_bounds__(256) rmsprop_apply_kernel(OptState o) {
   pdl_prologue();
   __shared__ float red[8];
   __shared__ float s_scale;
+  // data-parallel: barrier 1 of the peer exchange -- every peer has delivered its slice of the summed gradients and
+  // its partial norms into this rank's buffers (peer.cu)
+  if (o.wait_flags)
+    for (int part = 0; part < o.wait_parts; ++part)
+      wait_peers(o.wait_flags, 2 * part + 1, o.wait_world, o.wait_epoch[4 * part + 1], o.wait_err);
   float acc = 0.f;
-  for (int i = threadIdx.x; i < o.nblk; i += blockDim.x) acc += o.norm_partials[i];
+  for (int i = threadIdx.x; i < o.npart; i += blockDim.x) acc += o.norm_partials[i];
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
@@ -82,6 +88,11 @@ __global__ void __launch_bounds__(256) rmsprop_apply_kernel(OptState o) {
     gg = g.w * scale; m.w += (gg * gg - m.w) * (1.0f - 0.99f); w.w -= lr * gg / sqrtf(m.w + 0.1f);
     m4[i] = m; w4[i] = w;
   }
+}
+
+int optimizer_update_only(cudaStream_t s, const OptState& o) {
+  DRL_CUDA_CHECK((launch_k(rmsprop_apply_kernel, o.nblk, 256, 0, s, o)));
+  return DRL_OK;
 }
 
 int optimizer_apply(cudaStream_t s, const OptState& o) {

@@ -49,6 +49,8 @@ class NativeLearner:
         self._keep = [None] * self.num_slots     # host arrays referenced by in-flight H2D copies
         self._bucket = None
         self._ext_stream = None
+        self._peer = False
+        self._no_collective = False          # diagnostic only (bench.py --collective none)
 
     # ---- lifetime ----------------------------------------------------------------
     def close(self):
@@ -109,7 +111,7 @@ class NativeLearner:
 
     def step(self, slot=0):
         """sess.run([... train_op]) of agent/impala.py:144-146 on a staged slot."""
-        if self._distributed():
+        if self._distributed() and not self._peer:
             self.step_async(slot)
             return self.wait()
         o = N.StepOut()
@@ -117,7 +119,9 @@ class NativeLearner:
         return self._out(o)
 
     def step_async(self, slot=0):
-        if self._distributed():
+        if self._peer or self._no_collective:   # peer: the exchange is part of the step's CUDA graph (csrc/peer.cu)
+            N.check(N.lib.drl_learner_step_async(self._h, slot))
+        elif self._distributed():
             N.check(N.lib.drl_learner_forward_backward(self._h, slot))
             self._allreduce_bucket()
             N.check(N.lib.drl_learner_apply(self._h))
@@ -200,6 +204,26 @@ class NativeLearner:
         except Exception:      # pragma: no cover
             return False
         return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+    def enable_peer_exchange(self, group=None):
+        """Replace the NCCL all-reduce of the gradient bucket by the fused exchange over NVLink peer memory
+        (csrc/peer.cu): the ranks of ONE node swap CUDA-IPC handles here (a 128-byte all_gather), after which
+        forward, backward, exchange and update run as one CUDA graph.  Collective: every rank must call it."""
+        import torch
+        import torch.distributed as dist
+        if not self._distributed():
+            raise RuntimeError("enable_peer_exchange needs an initialised process group with world_size > 1")
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        mine = np.zeros(128, np.uint8)
+        N.check(N.lib.drl_learner_peer_export(self._h, N.ptr(mine), mine.size))
+        dev = torch.device("cuda", self.device)
+        t = torch.from_numpy(mine).to(dev)
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t, group=group)
+        allh = np.ascontiguousarray(torch.stack(parts).cpu().numpy())
+        N.check(N.lib.drl_learner_peer_import(self._h, rank, world, N.ptr(allh), allh.size))
+        dist.barrier(group=group)
+        self._peer = True
 
     def bucket_tensor(self):
         """torch view (no copy) of the device gradient bucket [padded grads | 3 loss sums | pad]."""

@@ -122,6 +122,16 @@ int drl_learner_wait(drl_learner* h, drl_step_out* out);
 int drl_learner_forward_backward(drl_learner* h, int32_t slot);
 int drl_learner_grad_bucket(drl_learner* h, void** dev_ptr, int64_t* count);
 int drl_learner_apply(drl_learner* h);          /* async; follow with drl_learner_wait */
+/* (new) Gradient exchange over NVLink peer memory, fused with the global-norm partials, INSTEAD of an all-reduce of
+ * the bucket (one process per GPU on one node; buffers shared through CUDA IPC).  Every rank calls peer_export (128
+ * bytes out: IPC handles of its bucket and of its exchange buffer), the ranks all-gather those blobs by any means
+ * (torch.distributed in learner.py), then every rank calls peer_import with the world x 128 bytes in rank order.
+ * From then on drl_learner_step / _step_async / _apply perform the exchange themselves inside the step's CUDA graph:
+ * device-side barrier, each rank sums its slice of every rank's bucket in rank order and delivers it to every rank
+ * (bit-identical replicas), barrier, clip + RMSProp.  Do not all-reduce the bucket as well.  All ranks must step in
+ * lockstep; a rank that never arrives is reported by drl_learner_wait after a 20 s device-side time-out. */
+int drl_learner_peer_export(drl_learner* h, void* handles, int64_t bytes);
+int drl_learner_peer_import(drl_learner* h, int32_t rank, int32_t world, const void* all_handles, int64_t bytes);
 /* The handle's compute stream (cudaStream_t as void*), for ordering external work (NCCL). */
 int drl_learner_stream(drl_learner* h, void** stream);
 

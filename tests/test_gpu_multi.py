@@ -26,7 +26,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, peer=False):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -38,9 +38,15 @@ def _worker(rank, world, port, out_dir):
     sh = synthetic.slice_batch(batch, lo, hi)
     eng = parity.native_learner(sh, params, cfg, device=rank)
     eng.stage(0, *[sh[k] for k in synthetic.TRAIN_FIELDS])
+    if peer:
+        eng.enable_peer_exchange()          # the exchange becomes part of the step (csrc/peer.cu)
     out = eng.step(0)                       # forward_backward -> all_reduce(SUM) -> apply
-    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), grads=eng.get_grads(), params=eng.get_params(),
-             losses=np.array([out["pi_loss"], out["baseline_loss"], out["entropy"], out["grad_norm"]]))
+    grads, params1 = eng.get_grads(), eng.get_params()
+    out2 = eng.step(0)                      # a second step: barrier epochs, buffer reuse
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), grads=grads, params=params1, params2=eng.get_params(),
+             losses=np.array([out["pi_loss"], out["baseline_loss"], out["entropy"], out["grad_norm"]]),
+             losses2=np.array([out2["pi_loss"], out2["baseline_loss"], out2["entropy"], out2["grad_norm"]]))
+    dist.barrier()                          # nobody unmaps / frees while a peer may still read
     eng.close()
     dist.barrier()
     dist.destroy_process_group()
@@ -65,3 +71,30 @@ def test_two_gpu_allreduce_step_equals_single_replica(native, tmp_path):
     assert np.all(np.abs(r0["losses"] - ref) <= parity.TOL * np.abs(ref))
     p0 = it.flatten_params(params)
     assert np.max(np.abs((r0["params"] - p0) - (p1 - p0))) <= 1e-3 * np.max(np.abs(p1 - p0))
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_fused_peer_exchange_equals_nccl_path(native, tmp_path, world):
+    """The exchange as kernels over NVLink peer memory (CUDA IPC; csrc/peer.cu) inside the step graph: all ranks end
+    with bit-identical replicas, and gradients / losses / parameters equal the NCCL all-reduce path over two steps."""
+    if native.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    import torch.multiprocessing as mp
+    d_nccl, d_peer = tmp_path / "nccl", tmp_path / "peer"
+    d_nccl.mkdir()
+    d_peer.mkdir()
+    mp.spawn(_worker, args=(world, _free_port(), str(d_nccl), False), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(d_peer), True), nprocs=world, join=True)
+    n0 = np.load(d_nccl / "rank0.npz")
+    p0 = np.load(d_peer / "rank0.npz")
+    for r in range(1, world):
+        pr = np.load(d_peer / ("rank%d.npz" % r))
+        for k in ("grads", "params", "params2", "losses", "losses2"):
+            assert np.array_equal(p0[k], pr[k]), (r, k)               # replicas stay bit-identical
+    if world == 2:
+        assert np.array_equal(p0["grads"], n0["grads"])               # a + b in rank order, like the 2-rank all-reduce
+    else:
+        assert parity.rel_err(p0["grads"], n0["grads"]) < 1e-6        # NCCL's summation order differs for W > 2
+    assert np.allclose(p0["losses"], n0["losses"], rtol=1e-6) and np.allclose(p0["losses2"], n0["losses2"], rtol=1e-5)
+    upd = np.max(np.abs(n0["params2"] - it.flatten_params(parity.make_case(B, T, A, seed=77)[1])))
+    assert np.max(np.abs(p0["params2"] - n0["params2"])) <= 1e-4 * upd

@@ -25,9 +25,19 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--collective", choices=["peer", "nccl"], default="peer", help="under torchrun (N > 1)")
     a = ap.parse_args()
     B, T = a.batch, 20
-    eng = NativeLearner(batch=B, trajectory=T, num_action=18, use_cuda_graph=not a.no_graph, math_mode=a.math_mode)
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    eng = NativeLearner(batch=B, trajectory=T, num_action=18, use_cuda_graph=not a.no_graph, math_mode=a.math_mode,
+                        device=local)
+    if world > 1 and a.collective == "peer":
+        eng.enable_peer_exchange()
     bt = synth_batch(B, 1)
     fields = ("state", "reward", "action", "done", "behavior_policy", "previous_action", "initial_h", "initial_c")
     for s in range(2):
@@ -40,6 +50,9 @@ def main():
     for i in range(a.steps):
         buf.zero_()
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
         eng.step(i % 2)
         torch.cuda.synchronize()
         h = buf.cpu().numpy()
@@ -47,6 +60,13 @@ def main():
         rec = sorted((int(h[1 + 2 * j]), int(h[2 + 2 * j])) for j in range(n))
         per_step.append(rec)
     N.check(N.lib.drl_debug_trace(C.c_void_p(0)))
+    if world > 1:
+        dist.barrier()
+        eng.close()
+        dist.barrier()
+        dist.destroy_process_group()
+        if rank != 0:
+            return
     rec = per_step[-1]
     t0 = rec[0][0]
     print("# %d kernels, first start -> last start %.1f us (steps: %s)" % (
