@@ -96,8 +96,8 @@ struct drl_learner {
   OptState opt{};
   long long* d_step = nullptr;
   float* d_lr = nullptr;
-  float* d_out = nullptr;
-  float* h_out = nullptr;    // pinned [8]
+  float* d_out = nullptr;    // device alias of h_out (mapped pinned memory)
+  float* h_out = nullptr;    // pinned [8]: the step's scalars, written by the update kernel itself (zero-copy)
   float* h_flat = nullptr;   // pinned scratch for set/get params (padded_total floats)
   std::vector<Slot> slots;
   std::vector<void*> allocs;
@@ -197,14 +197,13 @@ int enqueue_apply(drl_learner* h, bool local_only = false) {
     prof_mark(h->compute, "optimizer(rmsprop)");
     DRL_TRY(optimizer_update_only(h->compute, h->plan.o));
     prof_mark(h->compute, "end");
-    DRL_CUDA_CHECK(cudaMemcpyAsync(h->h_peer_err, h->comm + h->off_err, sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                                   h->compute));
   } else {
     prof_mark(h->compute, "optimizer(norm+rmsprop)");
     DRL_TRY(optimizer_apply(h->compute, h->opt));
     prof_mark(h->compute, "end");
   }
-  DRL_CUDA_CHECK(cudaMemcpyAsync(h->h_out, h->d_out, 8 * sizeof(float), cudaMemcpyDeviceToHost, h->compute));
+  // no D2H copy node: the update kernel stores the 8 scalars straight into mapped pinned memory (h_out); a memcpy
+  // at the end of the graph sat in the ~20 us gap between two steps (tools/timeline.py --back-to-back)
   return DRL_OK;
 }
 
@@ -411,8 +410,8 @@ int drl_learner_create(const drl_learner_config* cfg, drl_learner** out) {
     v.loss_sums = h->bucket + NP;
     DRL_TRY(dev_alloc(h, &h->d_step, 1));
     DRL_TRY(dev_alloc(h, &h->d_lr, 1));
-    DRL_TRY(dev_alloc(h, &h->d_out, 8));
-    DRL_CUDA_CHECK(cudaHostAlloc((void**)&h->h_out, 8 * sizeof(float), cudaHostAllocDefault));
+    DRL_CUDA_CHECK(cudaHostAlloc((void**)&h->h_out, 8 * sizeof(float), cudaHostAllocMapped));
+    DRL_CUDA_CHECK(cudaHostGetDevicePointer((void**)&h->d_out, h->h_out, 0));
     DRL_CUDA_CHECK(cudaHostAlloc((void**)&h->h_flat, NP * sizeof(float), cudaHostAllocDefault));
     memset(h->h_out, 0, 8 * sizeof(float));
     OptState& o = h->opt;
@@ -607,7 +606,7 @@ int drl_learner_peer_export(drl_learner* h, void* handles, int64_t bytes) {
     h->comm_bytes = h->off_err + 256;
     DRL_CUDA_CHECK(cudaMalloc((void**)&h->comm, h->comm_bytes));
     DRL_CUDA_CHECK(cudaMemset(h->comm, 0, h->comm_bytes));
-    DRL_CUDA_CHECK(cudaHostAlloc((void**)&h->h_peer_err, sizeof(uint32_t), cudaHostAllocDefault));
+    DRL_CUDA_CHECK(cudaHostAlloc((void**)&h->h_peer_err, sizeof(uint32_t), cudaHostAllocMapped));   // zero-copy too
     *h->h_peer_err = 0;
   }
   cudaIpcMemHandle_t hd[2];
@@ -645,6 +644,7 @@ int drl_learner_peer_import(drl_learner* h, int32_t rank, int32_t world, const v
     h->plan.t.epoch[p] = reinterpret_cast<uint32_t*>(comm + h->off_epoch);
     h->plan.t.err[p] = reinterpret_cast<uint32_t*>(comm + h->off_err);
   }
+  DRL_CUDA_CHECK(cudaHostGetDevicePointer((void**)&h->plan.t.err[rank], h->h_peer_err, 0));   // own entry: host-visible
   h->plan.rank = rank;
   h->plan.world = world;
   h->plan.nblk = h->peer_nblk;

@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--collective", choices=["peer", "nccl"], default="peer", help="under torchrun (N > 1)")
+    ap.add_argument("--back-to-back", action="store_true",
+                    help="enqueue all steps without host synchronisation (steady state) and print the last one")
     a = ap.parse_args()
     B, T = a.batch, 20
     world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
@@ -47,7 +49,26 @@ def main():
     buf = torch.zeros(8001, dtype=torch.int64, device="cuda")
     N.check(N.lib.drl_debug_trace(C.c_void_p(buf.data_ptr())))
     per_step = []
-    for i in range(a.steps):
+    if a.back_to_back:
+        nsteps = max(a.steps, 6)
+        buf.zero_()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+        for i in range(nsteps):
+            eng.step_async(i % 2)
+        eng.wait()
+        torch.cuda.synchronize()
+        h = buf.cpu().numpy()
+        n = int(h[0])
+        rec = sorted((int(h[1 + 2 * j]), int(h[2 + 2 * j])) for j in range(n))
+        per = n // nsteps
+        per_step = [rec[k * per:(k + 1) * per] for k in range(nsteps)]
+        print("# back-to-back: step periods (first kernel to first kernel, us): %s" % ", ".join(
+            "%.1f" % ((per_step[k + 1][0][0] - per_step[k][0][0]) / 1e3) for k in range(nsteps - 1)))
+        per_step = per_step[:-1] if False else per_step
+    for i in range(0 if a.back_to_back else a.steps):
         buf.zero_()
         torch.cuda.synchronize()
         if world > 1:
