@@ -269,7 +269,8 @@ def run_ours(args):
                         math_mode=args.math_mode)
     eng.set_params(model.init_params(seed=0))
     if world > 1 and args.collective == "peer":
-        eng.enable_peer_exchange()
+        if not eng.enable_peer_exchange():       # some rank could not map a peer: every rank stays on NCCL
+            args.collective = "nccl"
     eng._no_collective = world > 1 and args.collective == "none"
     ext = torch.cuda.ExternalStream(eng.stream_ptr(), device="cuda:%d" % local)
 

@@ -76,6 +76,7 @@ def _load():
         "drl_learner_stream": (C.c_int, [vp, C.POINTER(vp)]),
         "drl_learner_peer_export": (C.c_int, [vp, vp, i64]),
         "drl_learner_peer_import": (C.c_int, [vp, i32, i32, vp, i64]),
+        "drl_learner_peer_disable": (C.c_int, [vp]),
         "drl_learner_forward": (C.c_int, [vp, i32, vp, vp]),
         "drl_learner_taps": (C.c_int, [vp, vp, vp, vp, vp]),
         "drl_learner_read_buffer": (C.c_int, [vp, C.c_char_p, vp, i64]),

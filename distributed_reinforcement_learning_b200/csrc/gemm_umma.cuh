@@ -7,18 +7,20 @@
 // all three products accumulate in fp32 in ONE TMEM accumulator.  Same loader / epilogue functor
 // concepts as gemm_simt.cuh, so every layer of layers.cu can run on either core.
 //
-// Structure (one 128 x BN output tile per CTA, 160 threads, 1 CTA per SM):
+// Structure (one 128 x BN output tile per CTA; 160-320 threads; 1-3 CTAs per SM depending on the configuration):
 //   warps 0..PW-1 (PW = 4 or 8): PRODUCERS, then EPILOGUE.  Each thread gathers float4 groups of A and B through the
-//               loader functors (im2col, concat, transposes happen here -- which is why TMA cannot
-//               stage these operands), splits them into hi/lo and writes both into the stage's
-//               shared-memory operand tiles in the canonical 128-byte-swizzled UMMA layout
-//               (K-major for kContigK loaders, MN-major otherwise), then fence.proxy.async and
-//               mbarrier-arrive on full[stage].
+//               loader functors (im2col, concat, transposes, uint8 -> fp32 happen here), splits them into hi/lo and
+//               writes both into the stage's shared-memory operand tiles in the canonical swizzled UMMA layout
+//               (K-major for kContigK loaders, MN-major otherwise), then fence.proxy.async and mbarrier-arrive on
+//               full[stage].  A weight operand may instead arrive as a pre-split, pre-tiled image with one
+//               cp.async.bulk per stage (PretiledB; issued by warp PW+1 when Cfg::LW).
 //   warp PW   : TMEM allocation + MMA ISSUER: waits full[stage], one lane issues 3 x (BK/8)
 //               tcgen05.mma (M=128, N=BN, K=8) from shared-memory descriptors, then tcgen05.commit ->
 //               empty[stage]; after the last K tile tcgen05.commit -> acc_full.
-//   epilogue  : warps 0-3 read their 32 TMEM lanes (tcgen05.ld 32x32b.x32) and hand rows to the
-//               epilogue functor (bias/ReLU/mask/split-K partial ...).
+//   epilogue  : the producer warps read their 32 TMEM lanes (tcgen05.ld 32x32b.x32), transpose each 32x32 block
+//               through a swizzled shared tile (epilogue_store_32x32) and hand row segments to the epilogue
+//               functor (bias/ReLU/mask/split-K partial ...).
+// gemm_tma.cuh holds the TMA-fed variant (cp.async.bulk.tensor im2col boxes) for the conv2/conv3 forward.
 //
 // Canonical SWIZZLE_128B layouts (CuTe mma_traits_sm100.hpp::make_umma_desc), BK = 32 floats:
 //   K-major : row r is 128 contiguous bytes (32 floats of K) at r*128; the 16-byte chunk c of row r is

@@ -171,9 +171,9 @@ void weight_image_sizes(size_t (&b)[WeightImages::kCount]) {
   b[6] = weight_image_bytes<256>(512, 64);
 }
 
-// Refresh the weight images (7 small launches; ~60 MB written).  Must run after every parameter change.
-// Only the big weight operands are pre-tiled (LSTM forward/dgrad, the dCol GEMMs): for the conv-forward GEMMs the
-// weight tile is a small part of a stage and pre-tiling it measured no gain (images 0-2 stay unused).
+// Refresh the weight images (4 launches on the side stream + 1 for the two conv-forward images; ~60 MB written).
+// Must run after every parameter change.  Image 0 (conv1) is unused: conv1 is the first kernel of the step and its
+// weight tile is 1/5 of a stage.
 int net_retile(cudaStream_t, cudaStream_t s_rest, const ParamLayout& pl, const float* P, const WeightImages& wi) {
   prof_mark(s_rest, "weight_retile");
   DRL_TRY((launch_retile_b<256>(s_rest, PlainB{P + pl.lstm_w, Geo::G4, 0}, Geo::G4, Geo::XK, wi.img[3])));

@@ -303,7 +303,7 @@ int drl_debug_trace(void* dev_buf) {
   DRL_CUDA_CHECK(cudaDeviceSynchronize());
   return DRL_OK;
 }
-const char* drl_version(void) { return "drl_b200 0.1 (sm_100a; FP32-FFMA gather-GEMM path)"; }
+const char* drl_version(void) { return "drl_b200 0.2 (sm_100a; tcgen05 3xTF32 gather-GEMM, FP32-FFMA fallback core, NVLink peer exchange)"; }
 
 int drl_device_count(void) {
   int n = 0;
@@ -663,6 +663,21 @@ int drl_learner_peer_import(drl_learner* h, int32_t rank, int32_t world, const v
   for (auto& g : h->graph_step) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
   if (h->graph_apply) { cudaGraphExecDestroy(h->graph_apply); h->graph_apply = nullptr; }
   h->peer_on = true;
+  return DRL_OK;
+}
+
+int drl_learner_peer_disable(drl_learner* h) {
+  DRL_TRY(check_handle(h));
+  DRL_TRY(set_device(h));
+  DRL_CUDA_CHECK(cudaDeviceSynchronize());
+  for (void* p : h->peer_opened) cudaIpcCloseMemHandle(p);
+  h->peer_opened.clear();
+  cudaGetLastError();
+  if (h->peer_on) {
+    for (auto& g : h->graph_step) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+    if (h->graph_apply) { cudaGraphExecDestroy(h->graph_apply); h->graph_apply = nullptr; }
+  }
+  h->peer_on = false;
   return DRL_OK;
 }
 

@@ -34,6 +34,77 @@ __device__ __forceinline__ float clip_reward(float r, int mode) {
   return ((r < 0.f) ? 0.3f * sq : sq) * 5.0f;
 }
 
+// One trajectory b, one warp, lane = time step: both V-trace windows, pg_advantage, the three loss terms of this
+// trajectory's steps and dL/dlogits, dL/dV.  policy / value are addressed as base + t * stride so that the same code
+// reads them from global memory (rows m = t*B + b) or from a CTA's shared-memory copy.
+__device__ __forceinline__ void vtrace_trajectory(const VtraceCfg& cfg, const float* pol_base, int pol_stride,
+                                                  const float* val_base, int val_stride, const Inputs& in,
+                                                  const VtraceOut& out, float* __restrict__ dlogits,
+                                                  float* __restrict__ dv, int b, int B, int T, int A, int lane,
+                                                  float& l_pg, float& l_bl, float& l_en) {
+  const int Tp = T - 2;
+  const int t = lane;
+  const bool live = t < T;
+  const int m = live ? t * B + b : 0;       // time-major activation row
+  const int src = live ? b * T + t : 0;     // batch-major input index
+  const float* prow = pol_base + (size_t)(live ? t : 0) * pol_stride;
+  float V = 0.f, rew = 0.f, gam = 0.f, rhob = 0.f, pi_a = 1.f;
+  int act = 0;
+  if (live) {
+    V = val_base[(size_t)t * val_stride];
+    act = in.action[src];
+    rew = clip_reward(in.reward[src], cfg.reward_clipping);
+    gam = in.done[src] ? 0.f : cfg.discount;                               // agent/impala.py:51
+    pi_a = prow[act];
+    const float mu_a = in.mu[(size_t)src * A + act];
+    const float log_rho = logf(pi_a) - logf(mu_a);                         // optimizer/vtrace.py:46-51
+    const float rho = expf(log_rho);                                       // :74
+    rhob = fminf(1.0f, rho);                                               // :75-80 (clip_rho = cs = min(1, rho))
+  }
+  const float Vn = __shfl_down_sync(0xffffffffu, V, 1);
+  const float delta = (t <= T - 2) ? rhob * (rew + gam * Vn - V) : 0.f;    // :84
+  const float gc = gam * rhob;
+  // window 1: steps 1..T-2 (bootstrap V_{T-1}); window 0: steps 0..T-3 (bootstrap V_{T-2})
+  float a1 = (t <= T - 2) ? gc : 0.f, b1 = (t <= T - 2) ? delta : 0.f;
+  float a0 = (t <= T - 3) ? gc : 0.f, b0 = (t <= T - 3) ? delta : 0.f;
+  warp_affine_suffix_scan(a1, b1, lane);
+  warp_affine_suffix_scan(a0, b0, lane);
+  const float vs = V + b0;                                                 // :101
+  const float vs1 = V + b1;
+  const float vs1n = __shfl_down_sync(0xffffffffu, vs1, 1);               // vs_plus_1 at this step
+  if (t < Tp) {
+    const float adv = rhob * (rew + gam * vs1n - V);                       // agent/impala.py:78-80
+    const size_t o = (size_t)b * Tp + t;
+    out.vs[o] = vs;
+    out.clipped_rho[o] = rhob;
+    out.vs_plus_1[o] = vs1n;
+    out.pg_adv[o] = adv;
+    // losses (optimizer/vtrace.py:105-126)
+    l_pg = -logf(pi_a + 1e-8f) * adv;
+    const float err = vs - V;
+    l_bl = 0.5f * err * err;
+    // gradients wrt logits through softmax:  g_k = dL/dpi_k ; dlogit_k = pi_k (g_k - sum_j pi_j g_j)
+    float s = 0.f, ent = 0.f;
+    for (int k = 0; k < A; ++k) {
+      const float p = prow[k];
+      const float lp = logf(p);
+      ent += p * lp;
+      float g = cfg.entropy_coef * (lp + 1.0f);
+      if (k == act) g -= adv / (p + 1e-8f);
+      s += p * g;
+    }
+    l_en = ent;
+    float* drow = dlogits + (size_t)m * 32;
+    for (int k = 0; k < A; ++k) {
+      const float p = prow[k];
+      float g = cfg.entropy_coef * (logf(p) + 1.0f);
+      if (k == act) g -= adv / (p + 1e-8f);
+      drow[k] = p * (g - s);
+    }
+    dv[(size_t)m * 32] = -cfg.baseline_coef * err;
+  }
+}
+
 __global__ void __launch_bounds__(128) vtrace_losses_kernel(
     VtraceCfg cfg, const float* __restrict__ policy, const float* __restrict__ value, Inputs in, VtraceOut out,
     float* __restrict__ dlogits, float* __restrict__ dv, int B, int T, int A) {
@@ -42,71 +113,10 @@ __global__ void __launch_bounds__(128) vtrace_losses_kernel(
   __shared__ bool is_last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * 4 + warp;
-  const int Tp = T - 2;
   float l_pg = 0.f, l_bl = 0.f, l_en = 0.f;
-
-  if (b < B) {
-    const int t = lane;
-    const bool live = t < T;
-    const int m = live ? t * B + b : 0;       // time-major activation row
-    const int src = live ? b * T + t : 0;     // batch-major input index
-    float V = 0.f, rew = 0.f, gam = 0.f, rhob = 0.f, pi_a = 1.f;
-    int act = 0;
-    if (live) {
-      V = value[m];
-      act = in.action[src];
-      rew = clip_reward(in.reward[src], cfg.reward_clipping);
-      gam = in.done[src] ? 0.f : cfg.discount;                               // agent/impala.py:51
-      pi_a = policy[(size_t)m * A + act];
-      const float mu_a = in.mu[(size_t)src * A + act];
-      const float log_rho = logf(pi_a) - logf(mu_a);                         // optimizer/vtrace.py:46-51
-      const float rho = expf(log_rho);                                       // :74
-      rhob = fminf(1.0f, rho);                                               // :75-80 (clip_rho = cs = min(1, rho))
-    }
-    const float Vn = __shfl_down_sync(0xffffffffu, V, 1);
-    const float delta = (t <= T - 2) ? rhob * (rew + gam * Vn - V) : 0.f;    // :84
-    const float gc = gam * rhob;
-    // window 1: steps 1..T-2 (bootstrap V_{T-1}); window 0: steps 0..T-3 (bootstrap V_{T-2})
-    float a1 = (t <= T - 2) ? gc : 0.f, b1 = (t <= T - 2) ? delta : 0.f;
-    float a0 = (t <= T - 3) ? gc : 0.f, b0 = (t <= T - 3) ? delta : 0.f;
-    warp_affine_suffix_scan(a1, b1, lane);
-    warp_affine_suffix_scan(a0, b0, lane);
-    const float vs = V + b0;                                                 // :101
-    const float vs1 = V + b1;
-    const float vs1n = __shfl_down_sync(0xffffffffu, vs1, 1);               // vs_plus_1 at this step
-    if (t < Tp) {
-      const float adv = rhob * (rew + gam * vs1n - V);                       // agent/impala.py:78-80
-      const size_t o = (size_t)b * Tp + t;
-      out.vs[o] = vs;
-      out.clipped_rho[o] = rhob;
-      out.vs_plus_1[o] = vs1n;
-      out.pg_adv[o] = adv;
-      // losses (optimizer/vtrace.py:105-126)
-      l_pg = -logf(pi_a + 1e-8f) * adv;
-      const float err = vs - V;
-      l_bl = 0.5f * err * err;
-      // gradients wrt logits through softmax:  g_k = dL/dpi_k ; dlogit_k = pi_k (g_k - sum_j pi_j g_j)
-      const float* prow = policy + (size_t)m * A;
-      float s = 0.f, ent = 0.f;
-      for (int k = 0; k < A; ++k) {
-        const float p = prow[k];
-        const float lp = logf(p);
-        ent += p * lp;
-        float g = cfg.entropy_coef * (lp + 1.0f);
-        if (k == act) g -= adv / (p + 1e-8f);
-        s += p * g;
-      }
-      l_en = ent;
-      float* drow = dlogits + (size_t)m * 32;
-      for (int k = 0; k < A; ++k) {
-        const float p = prow[k];
-        float g = cfg.entropy_coef * (logf(p) + 1.0f);
-        if (k == act) g -= adv / (p + 1e-8f);
-        drow[k] = p * (g - s);
-      }
-      dv[(size_t)m * 32] = -cfg.baseline_coef * err;
-    }
-  }
+  if (b < B)
+    vtrace_trajectory(cfg, policy + (size_t)b * A, B * A, value + b, B, in, out, dlogits, dv, b, B, T, A, lane, l_pg,
+                      l_bl, l_en);
   // ---- deterministic loss reduction: warp -> block -> last block sums the block partials -----
   l_pg = warp_sum(l_pg); l_bl = warp_sum(l_bl); l_en = warp_sum(l_en);
   if (lane == 0) { red[warp][0] = l_pg; red[warp][1] = l_bl; red[warp][2] = l_en; }

@@ -208,22 +208,31 @@ class NativeLearner:
     def enable_peer_exchange(self, group=None):
         """Replace the NCCL all-reduce of the gradient bucket by the fused exchange over NVLink peer memory
         (csrc/peer.cu): the ranks of ONE node swap CUDA-IPC handles here (a 128-byte all_gather), after which
-        forward, backward, exchange and update run as one CUDA graph.  Collective: every rank must call it."""
+        forward, backward, exchange and update run as one CUDA graph.  Collective: every rank must call it.
+        Returns True when every rank could map every peer; otherwise all ranks stay on the NCCL path (False)."""
         import torch
         import torch.distributed as dist
         if not self._distributed():
             raise RuntimeError("enable_peer_exchange needs an initialised process group with world_size > 1")
         rank, world = dist.get_rank(group), dist.get_world_size(group)
-        mine = np.zeros(128, np.uint8)
-        N.check(N.lib.drl_learner_peer_export(self._h, N.ptr(mine), mine.size))
         dev = torch.device("cuda", self.device)
+        mine = np.zeros(128, np.uint8)
+        ok = N.lib.drl_learner_peer_export(self._h, N.ptr(mine), mine.size) == 0
         t = torch.from_numpy(mine).to(dev)
         parts = [torch.empty_like(t) for _ in range(world)]
         dist.all_gather(parts, t, group=group)
         allh = np.ascontiguousarray(torch.stack(parts).cpu().numpy())
-        N.check(N.lib.drl_learner_peer_import(self._h, rank, world, N.ptr(allh), allh.size))
+        ok = ok and N.lib.drl_learner_peer_import(self._h, rank, world, N.ptr(allh), allh.size) == 0
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)       # all or nobody
+        if int(flag.item()) == 0:
+            N.lib.drl_learner_peer_disable(self._h)
+            dist.barrier(group=group)
+            self._peer = False
+            return False
         dist.barrier(group=group)
         self._peer = True
+        return True
 
     def bucket_tensor(self):
         """torch view (no copy) of the device gradient bucket [padded grads | 3 loss sums | pad]."""

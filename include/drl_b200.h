@@ -132,6 +132,8 @@ int drl_learner_apply(drl_learner* h);          /* async; follow with drl_learne
  * lockstep; a rank that never arrives is reported by drl_learner_wait after a 20 s device-side time-out. */
 int drl_learner_peer_export(drl_learner* h, void* handles, int64_t bytes);
 int drl_learner_peer_import(drl_learner* h, int32_t rank, int32_t world, const void* all_handles, int64_t bytes);
+/* Back to the local update (the caller all-reduces the bucket again); also the clean-up after a failed import. */
+int drl_learner_peer_disable(drl_learner* h);
 /* The handle's compute stream (cudaStream_t as void*), for ordering external work (NCCL). */
 int drl_learner_stream(drl_learner* h, void** stream);
 
