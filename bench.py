@@ -337,11 +337,18 @@ def run_ours(args):
     t0 = time.perf_counter()
     eng.stage(0, *hb[0])
     e2.record(ext)
+    per_slot = world == 1 or args.collective == "peer"     # the NCCL path keeps one result record: depth 1
     for i in range(K):
         eng.step_async(i % 2)
         if i + 1 < K:
             eng.stage((i + 1) % 2, *hb[(i + 1) % 3])     # H2D of step i+1 overlaps compute of step i
-        out = eng.wait()                                  # D2H read of this step's scalars
+        if per_slot:
+            if i >= 1:
+                out = eng.wait((i - 1) % 2)               # D2H read of step i-1's scalars while step i runs
+        else:
+            out = eng.wait()                              # D2H read of this step's scalars
+    if per_slot:
+        out = eng.wait((K - 1) % 2)
     e3.record(ext)
     barrier()
     wall_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
@@ -406,7 +413,8 @@ def run_ours(args):
                 "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,
                         "ms_per_step": ms_e2e / K, "wall_ms_per_step": wall_ms / K,
                         "path": "pinned ring -> drl_learner_stage (copy stream) -> drl_learner_step_async -> "
-                                "drl_learner_wait, double-buffered"},
+                                "drl_learner_wait_slot (every step's scalars are read on the host, one step behind: "
+                                "two steps in flight), double-buffered slots"},
                 "gpu_launches": launches, "clocks": clocks,
                 "last_step": {k: out[k] for k in ("pi_loss", "baseline_loss", "entropy", "grad_norm", "step")}}
         line.update(line_extra)

@@ -70,6 +70,7 @@ def _load():
         "drl_learner_step": (C.c_int, [vp, i32, C.POINTER(StepOut)]),
         "drl_learner_step_async": (C.c_int, [vp, i32]),
         "drl_learner_wait": (C.c_int, [vp, C.POINTER(StepOut)]),
+        "drl_learner_wait_slot": (C.c_int, [vp, i32, C.POINTER(StepOut)]),
         "drl_learner_forward_backward": (C.c_int, [vp, i32]),
         "drl_learner_grad_bucket": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i64)]),
         "drl_learner_apply": (C.c_int, [vp]),

@@ -97,7 +97,10 @@ struct drl_learner {
   long long* d_step = nullptr;
   float* d_lr = nullptr;
   float* d_out = nullptr;    // device alias of h_out (mapped pinned memory)
-  float* h_out = nullptr;    // pinned [8]: the step's scalars, written by the update kernel itself (zero-copy)
+  float* h_out = nullptr;    // pinned [num_slots + 1][8]: the steps' scalars, written by the update kernel itself
+                             // (zero-copy); row = slot for drl_learner_step*, row num_slots for drl_learner_apply
+  std::vector<cudaEvent_t> ev_done_slot;   // per result row
+  int last_out = 0;          // result row of the most recently enqueued update
   float* h_flat = nullptr;   // pinned scratch for set/get params (padded_total floats)
   std::vector<Slot> slots;
   std::vector<void*> allocs;
@@ -189,17 +192,19 @@ int enqueue_forward_backward(drl_learner* h, int slot) {
 }
 
 // local_only: the single-replica update on the local bucket even when the peer exchange is on (profiling on one rank)
-int enqueue_apply(drl_learner* h, bool local_only = false) {
+int enqueue_apply(drl_learner* h, int out_row, bool local_only = false) {
   pdl_break(h->compute);
+  OptState o_local = h->opt, o_peer = h->plan.o;
+  o_local.out = o_peer.out = h->d_out + 8 * out_row;
   if (h->peer_on && !local_only) {
     prof_mark(h->compute, "peer_exchange");
     DRL_TRY(peer_exchange(h->compute, h->plan, 0, 0, h->pl.padded_total / 4 + 1, true));   // grads + loss sums
     prof_mark(h->compute, "optimizer(rmsprop)");
-    DRL_TRY(optimizer_update_only(h->compute, h->plan.o));
+    DRL_TRY(optimizer_update_only(h->compute, o_peer));
     prof_mark(h->compute, "end");
   } else {
     prof_mark(h->compute, "optimizer(norm+rmsprop)");
-    DRL_TRY(optimizer_apply(h->compute, h->opt));
+    DRL_TRY(optimizer_apply(h->compute, o_local));
     prof_mark(h->compute, "end");
   }
   // no D2H copy node: the update kernel stores the 8 scalars straight into mapped pinned memory (h_out); a memcpy
@@ -239,7 +244,7 @@ int run_apply(drl_learner* h) {
     if (!h->graph_apply) {
       cudaGraph_t g = nullptr;
       DRL_CUDA_CHECK(cudaStreamBeginCapture(h->compute, cudaStreamCaptureModeThreadLocal));
-      int r = enqueue_apply(h);
+      int r = enqueue_apply(h, (int)h->slots.size());
       cudaError_t e = cudaStreamEndCapture(h->compute, &g);
       if (r != DRL_OK) { if (g) cudaGraphDestroy(g); return r; }
       if (e != cudaSuccess) { set_error("graph capture failed: %s", cudaGetErrorString(e)); return DRL_ERR_CUDA; }
@@ -248,41 +253,47 @@ int run_apply(drl_learner* h) {
     }
     DRL_CUDA_CHECK(cudaGraphLaunch(h->graph_apply, h->compute));
   } else {
-    DRL_TRY(enqueue_apply(h));
+    DRL_TRY(enqueue_apply(h, (int)h->slots.size()));
   }
+  h->last_out = (int)h->slots.size();
   DRL_CUDA_CHECK(cudaEventRecord(h->ev_stop, h->compute));
   DRL_CUDA_CHECK(cudaEventRecord(h->ev_done, h->compute));
+  DRL_CUDA_CHECK(cudaEventRecord(h->ev_done_slot[h->last_out], h->compute));
   h->pending = true;
   h->images_stale = true;
   return DRL_OK;
 }
 
-// Single-GPU step: nothing runs between the backward pass and the update, so both go into ONE graph per slot.
+// drl_learner_step*: nothing on the host runs between the backward pass and the update (at N > 1 the peer exchange
+// is part of the update), so both go into ONE graph per slot; the scalars land in the slot's own result row.
 int run_step(drl_learner* h, int slot) {
-  if (!h->cfg.use_cuda_graph) {
-    DRL_TRY(run_forward_backward(h, slot));
-    return run_apply(h);
-  }
   Slot& sl = h->slots[slot];
   if (!sl.has_data) { set_error("slot %d has not been staged", slot); return DRL_ERR_STATE; }
   DRL_CUDA_CHECK(cudaStreamWaitEvent(h->compute, sl.staged, 0));
   DRL_CUDA_CHECK(cudaEventRecord(h->ev_start, h->compute));
-  if (!h->graph_step[slot]) {
-    DRL_TRY(enqueue_forward_backward(h, slot));   // eager pass: per-kernel attributes are set outside of capture
-    cudaGraph_t g = nullptr;
-    DRL_CUDA_CHECK(cudaStreamBeginCapture(h->compute, cudaStreamCaptureModeThreadLocal));
-    int r = enqueue_forward_backward(h, slot);
-    if (r == DRL_OK) r = enqueue_apply(h);
-    cudaError_t e = cudaStreamEndCapture(h->compute, &g);
-    if (r != DRL_OK) { if (g) cudaGraphDestroy(g); return r; }
-    if (e != cudaSuccess) { set_error("graph capture failed: %s", cudaGetErrorString(e)); return DRL_ERR_CUDA; }
-    DRL_CUDA_CHECK(cudaGraphInstantiate(&h->graph_step[slot], g, 0));
-    cudaGraphDestroy(g);
+  if (h->cfg.use_cuda_graph) {
+    if (!h->graph_step[slot]) {
+      DRL_TRY(enqueue_forward_backward(h, slot));   // eager pass: per-kernel attributes are set outside of capture
+      cudaGraph_t g = nullptr;
+      DRL_CUDA_CHECK(cudaStreamBeginCapture(h->compute, cudaStreamCaptureModeThreadLocal));
+      int r = enqueue_forward_backward(h, slot);
+      if (r == DRL_OK) r = enqueue_apply(h, slot);
+      cudaError_t e = cudaStreamEndCapture(h->compute, &g);
+      if (r != DRL_OK) { if (g) cudaGraphDestroy(g); return r; }
+      if (e != cudaSuccess) { set_error("graph capture failed: %s", cudaGetErrorString(e)); return DRL_ERR_CUDA; }
+      DRL_CUDA_CHECK(cudaGraphInstantiate(&h->graph_step[slot], g, 0));
+      cudaGraphDestroy(g);
+    }
+    DRL_CUDA_CHECK(cudaGraphLaunch(h->graph_step[slot], h->compute));
+  } else {
+    DRL_TRY(enqueue_forward_backward(h, slot));
+    DRL_TRY(enqueue_apply(h, slot));
   }
-  DRL_CUDA_CHECK(cudaGraphLaunch(h->graph_step[slot], h->compute));
+  h->last_out = slot;
   DRL_CUDA_CHECK(cudaEventRecord(sl.consumed, h->compute));
   DRL_CUDA_CHECK(cudaEventRecord(h->ev_stop, h->compute));
   DRL_CUDA_CHECK(cudaEventRecord(h->ev_done, h->compute));
+  DRL_CUDA_CHECK(cudaEventRecord(h->ev_done_slot[slot], h->compute));
   h->pending = true;
   h->images_stale = true;
   return DRL_OK;
@@ -410,10 +421,13 @@ int drl_learner_create(const drl_learner_config* cfg, drl_learner** out) {
     v.loss_sums = h->bucket + NP;
     DRL_TRY(dev_alloc(h, &h->d_step, 1));
     DRL_TRY(dev_alloc(h, &h->d_lr, 1));
-    DRL_CUDA_CHECK(cudaHostAlloc((void**)&h->h_out, 8 * sizeof(float), cudaHostAllocMapped));
+    const size_t out_rows = (size_t)h->cfg.num_slots + 1;
+    DRL_CUDA_CHECK(cudaHostAlloc((void**)&h->h_out, out_rows * 8 * sizeof(float), cudaHostAllocMapped));
+    h->ev_done_slot.resize(out_rows, nullptr);
+    for (auto& e : h->ev_done_slot) DRL_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     DRL_CUDA_CHECK(cudaHostGetDevicePointer((void**)&h->d_out, h->h_out, 0));
     DRL_CUDA_CHECK(cudaHostAlloc((void**)&h->h_flat, NP * sizeof(float), cudaHostAllocDefault));
-    memset(h->h_out, 0, 8 * sizeof(float));
+    memset(h->h_out, 0, out_rows * 8 * sizeof(float));
     OptState& o = h->opt;
     o.params = h->params; o.ms = h->ms; o.grads = h->bucket; o.n = (int64_t)NP;
     o.nblk = 148 * 4;
@@ -483,6 +497,7 @@ int drl_learner_destroy(drl_learner* h) {
   if (h->ev_start) cudaEventDestroy(h->ev_start);
   if (h->ev_stop) cudaEventDestroy(h->ev_stop);
   if (h->ev_done) cudaEventDestroy(h->ev_done);
+  for (auto e : h->ev_done_slot) if (e) cudaEventDestroy(e);
   for (int i = 0; i < 8; ++i) if (h->fj[i]) cudaEventDestroy(h->fj[i]);
   if (h->side) cudaStreamDestroy(h->side);
   if (h->compute) cudaStreamDestroy(h->compute);
@@ -695,29 +710,42 @@ int drl_learner_step_async(drl_learner* h, int32_t slot) {
   return run_step(h, slot);
 }
 
-int drl_learner_wait(drl_learner* h, drl_step_out* out) {
-  DRL_TRY(check_handle(h));
-  if (!h->pending) { set_error("wait: no step in flight"); return DRL_ERR_STATE; }
-  DRL_TRY(set_device(h));
-  DRL_CUDA_CHECK(cudaEventSynchronize(h->ev_done));
-  h->pending = false;
+static int collect(drl_learner* h, int row, drl_step_out* out) {
+  DRL_CUDA_CHECK(cudaEventSynchronize(h->ev_done_slot[row]));
   if (h->peer_on && h->h_peer_err && *h->h_peer_err) {
     set_error("peer exchange: rank %d never reached the barrier (20 s)", (int)*h->h_peer_err - 1);
     return DRL_ERR_STATE;
   }
   if (out) {
-    out->pi_loss = h->h_out[0];
-    out->baseline_loss = h->h_out[1];
-    out->entropy = h->h_out[2];
-    out->learning_rate = h->h_out[3];
-    out->grad_norm = h->h_out[4];
-    out->total_loss = h->h_out[5];
+    const float* r = h->h_out + 8 * row;
+    out->pi_loss = r[0];
+    out->baseline_loss = r[1];
+    out->entropy = r[2];
+    out->learning_rate = r[3];
+    out->grad_norm = r[4];
+    out->total_loss = r[5];
     uint32_t lo, hi;
-    memcpy(&lo, &h->h_out[6], 4);
-    memcpy(&hi, &h->h_out[7], 4);
+    memcpy(&lo, &r[6], 4);
+    memcpy(&hi, &r[7], 4);
     out->step = (int64_t)(((uint64_t)hi << 32) | lo);
   }
   return DRL_OK;
+}
+
+int drl_learner_wait(drl_learner* h, drl_step_out* out) {
+  DRL_TRY(check_handle(h));
+  if (!h->pending) { set_error("wait: no step in flight"); return DRL_ERR_STATE; }
+  DRL_TRY(set_device(h));
+  h->pending = false;
+  return collect(h, h->last_out, out);
+}
+
+int drl_learner_wait_slot(drl_learner* h, int32_t slot, drl_step_out* out) {
+  DRL_TRY(check_handle(h));
+  if (slot < 0 || slot >= (int)h->slots.size()) { set_error("slot %d out of range", slot); return DRL_ERR_INVALID; }
+  DRL_TRY(set_device(h));
+  if (slot == h->last_out) h->pending = false;
+  return collect(h, slot, out);
 }
 
 int drl_learner_step(drl_learner* h, int32_t slot, drl_step_out* out) {
@@ -833,7 +861,7 @@ int drl_learner_profile_step(drl_learner* h, int32_t slot, char* names, int64_t 
   const bool par_saved = h->par;
   h->par = false;                       // serial: the event-to-event times are then per kernel
   int rc = enqueue_forward_backward(h, slot);
-  if (rc == DRL_OK) rc = enqueue_apply(h, /*local_only=*/true);   // one rank may profile alone
+  if (rc == DRL_OK) rc = enqueue_apply(h, (int)h->slots.size(), /*local_only=*/true);   // one rank may profile alone
   h->par = par_saved;
   g_prof.on = false;
   cudaError_t e = cudaStreamSynchronize(h->compute);

@@ -128,9 +128,14 @@ class NativeLearner:
         else:
             N.check(N.lib.drl_learner_step_async(self._h, slot))
 
-    def wait(self):
+    def wait(self, slot=None):
+        """Scalars of the last enqueued step; with `slot`, of the last step_async on that slot (each slot has its own
+        result record, so two steps can be in flight: read step i-1 while step i runs)."""
         o = N.StepOut()
-        N.check(N.lib.drl_learner_wait(self._h, C.byref(o)))
+        if slot is None:
+            N.check(N.lib.drl_learner_wait(self._h, C.byref(o)))
+        else:
+            N.check(N.lib.drl_learner_wait_slot(self._h, int(slot), C.byref(o)))
         return self._out(o)
 
     def forward_backward(self, slot=0):

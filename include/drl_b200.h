@@ -114,6 +114,9 @@ int drl_learner_step(drl_learner* h, int32_t slot, drl_step_out* out);
 /* Same, asynchronous: enqueue on the compute stream; drl_learner_wait collects the scalars. */
 int drl_learner_step_async(drl_learner* h, int32_t slot);
 int drl_learner_wait(drl_learner* h, drl_step_out* out);
+/* (new) Result of the most recent drl_learner_step_async on `slot` (blocks until that step is done).  Every slot has
+ * its own result record, so with two slots the host can keep two steps in flight and read step i-1 while step i runs. */
+int drl_learner_wait_slot(drl_learner* h, int32_t slot, drl_step_out* out);
 
 /* Data-parallel split of the step: forward+backward leaves the local gradient
  * sum in the bucket; the caller all-reduces (SUM) `count` floats at `dev_ptr` across ranks on

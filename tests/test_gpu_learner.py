@@ -166,3 +166,28 @@ def test_errors_are_loud(native):
             eng.stage(0, *[b[k] for k in synthetic.TRAIN_FIELDS])            # wrong batch size
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_two_steps_in_flight_per_slot_results(native, graph):
+    """drl_learner_wait_slot: every staging slot has its own result record, so the host can enqueue step i+1 before
+    it reads step i's scalars.  Results must equal the same two steps run one after the other."""
+    B, T, A = 4, 6, 18
+    batch, params, cfg = parity.make_case(B, T, A, seed=31)
+    b2 = synthetic.make_batch(B, T=T, A=A, seed=32)
+    seq = parity.native_learner(batch, params, cfg, use_cuda_graph=graph)
+    seq.stage(0, *[batch[k] for k in synthetic.TRAIN_FIELDS])
+    seq.stage(1, *[b2[k] for k in synthetic.TRAIN_FIELDS])
+    r0, r1 = seq.step(0), seq.step(1)
+    p_seq = seq.get_params()
+    seq.close()
+    eng = parity.native_learner(batch, params, cfg, use_cuda_graph=graph)
+    eng.stage(0, *[batch[k] for k in synthetic.TRAIN_FIELDS])
+    eng.stage(1, *[b2[k] for k in synthetic.TRAIN_FIELDS])
+    eng.step_async(0)
+    eng.step_async(1)            # second step enqueued before the first one's result is read
+    q0, q1 = eng.wait(0), eng.wait(1)
+    assert q0 == r0 and q1 == r1
+    assert q1["step"] == q0["step"] + 1
+    assert np.array_equal(eng.get_params(), p_seq)
+    eng.close()
