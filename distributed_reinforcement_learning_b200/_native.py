@@ -41,6 +41,18 @@ class StepOut(C.Structure):
                 ("step", C.c_int64)]
 
 
+class ApexConfig(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("height", C.c_int32), ("width", C.c_int32), ("channels", C.c_int32),
+                ("num_action", C.c_int32), ("discount_factor", C.c_float), ("start_learning_rate", C.c_float),
+                ("end_learning_rate", C.c_float), ("learning_frame", C.c_double), ("gradient_clip_norm", C.c_float),
+                ("reward_clipping", C.c_int32), ("device", C.c_int32), ("num_slots", C.c_int32),
+                ("use_cuda_graph", C.c_int32), ("math_mode", C.c_int32)]
+
+
+class ApexOut(C.Structure):
+    _fields_ = [("loss", C.c_float), ("learning_rate", C.c_float), ("grad_norm", C.c_float), ("step", C.c_int64)]
+
+
 class RingBatch(C.Structure):
     _fields_ = [("state", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p),
                 ("behavior_policy", C.c_void_p), ("action", C.c_void_p), ("previous_action", C.c_void_p),
@@ -99,6 +111,34 @@ def _load():
         "drl_ring_pop_batch": (C.c_int, [vp, C.POINTER(RingBatch), i32]),
         "drl_ring_release": (C.c_int, [vp, i32]),
         "drl_ring_size": (C.c_int, [vp]),
+        "drl_apex_create": (C.c_int, [C.POINTER(ApexConfig), C.POINTER(vp)]),
+        "drl_apex_destroy": (C.c_int, [vp]),
+        "drl_apex_param_count": (C.c_int, [vp, C.POINTER(i64)]),
+        "drl_apex_set_params": (C.c_int, [vp, i32, vp, i64]),
+        "drl_apex_get_params": (C.c_int, [vp, i32, vp, i64]),
+        "drl_apex_set_opt_state": (C.c_int, [vp, vp, vp, i64, i64, f32, f32]),
+        "drl_apex_get_opt_state": (C.c_int, [vp, vp, vp, i64, C.POINTER(i64), C.POINTER(f32), C.POINTER(f32)]),
+        "drl_apex_get_grads": (C.c_int, [vp, vp, i64]),
+        "drl_apex_target_to_main": (C.c_int, [vp]),
+        "drl_apex_stage": (C.c_int, [vp, i32] + [vp] * 7),
+        "drl_apex_step": (C.c_int, [vp, i32, C.POINTER(ApexOut), vp]),
+        "drl_apex_step_async": (C.c_int, [vp, i32]),
+        "drl_apex_wait": (C.c_int, [vp, C.POINTER(ApexOut), vp]),
+        "drl_apex_td_error": (C.c_int, [vp, i32] + [vp] * 7),
+        "drl_apex_act": (C.c_int, [vp, i32, vp, vp, vp]),
+        "drl_apex_taps": (C.c_int, [vp] * 6),
+        "drl_apex_read_buffer": (C.c_int, [vp, C.c_char_p, vp, i64]),
+        "drl_apex_profile_step": (C.c_int, [vp, i32, C.c_char_p, i64, vp, i32, C.POINTER(i32)]),
+        "drl_apex_last_step_ms": (C.c_int, [vp, C.POINTER(f32)]),
+        "drl_apex_launches_per_step": (C.c_int, [vp, C.POINTER(i32)]),
+        "drl_per_create": (C.c_int, [i64, C.POINTER(vp)]),
+        "drl_per_destroy": (C.c_int, [vp]),
+        "drl_per_add": (C.c_int, [vp, C.c_double, C.POINTER(i64)]),
+        "drl_per_sample": (C.c_int, [vp, i32, vp, vp, vp, vp, vp]),
+        "drl_per_update": (C.c_int, [vp, i64, C.c_double]),
+        "drl_per_total": (C.c_int, [vp, C.POINTER(C.c_double)]),
+        "drl_per_size": (C.c_int, [vp, C.POINTER(i64)]),
+        "drl_per_beta": (C.c_int, [vp, C.POINTER(C.c_double)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

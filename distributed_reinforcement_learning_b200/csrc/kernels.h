@@ -94,6 +94,10 @@ constexpr int kLstmSplits = 8;   // slabs allocated for the LSTM split-K partial
 // Per-kernel device timing (learner.cu): when a profile run is active, prof_mark records a CUDA event
 // on the launching stream before each named launch; otherwise it is a no-op.
 void prof_mark(cudaStream_t s, const char* name);
+// profile run bracket (shared by the IMPALA and the Ape-X learner): prof_begin arms prof_mark; prof_end synchronises
+// `s`, converts the recorded events into per-launch times (names joined by '\n') and disarms it.
+void prof_begin();
+int prof_end(cudaStream_t s, int rc, char* names, int64_t names_len, float* ms, int32_t max_kernels, int32_t* count);
 
 // Pre-split (hi/lo tf32), pre-tiled, pre-swizzled global copies of the weights that serve as B operands of the
 // tensor-core GEMMs (gemm_umma.cuh: PretiledB / retile_b_kernel); refreshed after every parameter update.

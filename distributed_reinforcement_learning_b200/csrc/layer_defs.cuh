@@ -1,0 +1,122 @@
+// layer_defs.cuh -- loader / tile-configuration instantiations, launch macros and split-K plans shared by the
+// IMPALA actor-critic (layers.cu) and the Ape-X dueling network (apex.cu): both run the same attention_CNN
+// (model/impala_actor_critic.py:5-10 == model/apex_value.py:4-9) through the same gather-GEMM kernels.
+#pragma once
+#include <algorithm>
+
+#include "gemm_simt.cuh"
+#include "gemm_umma.cuh"
+#include "gemm_tma.cuh"
+#include "gemm_umma_persist.cuh"
+#include "kernels.h"
+#include "loaders.cuh"
+
+namespace drl {
+
+// ------------------------------------------------------------------------------------------
+// Loader / epilogue instantiations for the three convolutions
+// ------------------------------------------------------------------------------------------
+using Conv1A = ConvFwdA<uint8_t, 84, 84, 4, 20, 20, 8, 4, true>;
+using Conv2A = ConvFwdA<float, 20, 20, 32, 9, 9, 4, 2, false>;
+using Conv3A = ConvFwdA<float, 9, 9, 64, 7, 7, 3, 1, false>;
+// math mode 4: TMA-fed forward of conv2 / conv3 (gemm_tma.cuh): tiles of 1 image (81 rows) / 2 images (98 rows), 4 stages.
+// Correct and tested, but measured SLOWER than the software producers on this network (conv2 59 vs 46 us, conv3 41 vs
+// 33 us at B=32, T=20): with 32/64 input channels a K tile is one filter tap, so every activation byte is fetched
+// 4x (conv2) / 9x (conv3) from L2 for each of the two planes plus a 16 KB weight tile per tap and image -- 2.3x the
+// L2->SM bytes of the LDG path, which reads raw fp32 once per tap and splits in registers.
+using Conv2Tma = ConvTmaCfg<32, 20, 9, 4, 2, 1, 4>;
+using Conv3Tma = ConvTmaCfg<64, 9, 7, 3, 1, 2, 4>;
+using Conv1WA = ConvWgradA<uint8_t, 84, 84, 4, 20, 20, 8, 4, true>;
+using Conv2WA = ConvWgradA<float, 20, 20, 32, 9, 9, 4, 2, false>;
+using Conv3WA = ConvWgradA<float, 9, 9, 64, 7, 7, 3, 1, false>;
+using Conv3DA = ConvDgradA<7, 7, 64, 1, 3, 3, 9, 9>;
+using Conv3DB = ConvDgradB<64, 64, 1, 3, 3>;
+using Conv3DE = EpConvDx<9, 9, 64, 1, 9, 9>;
+using Conv2DA = ConvDgradA<9, 9, 64, 2, 4, 4, 10, 10>;
+using Conv2DB = ConvDgradB<32, 64, 2, 4, 4>;
+using Conv2DE = EpConvDx<20, 20, 32, 2, 10, 10>;
+
+using U32 = UmmaCfg<32, 2, 3>;   // 24 KB / stage (A exact: conv1 only), 3 CTAs per SM
+using U64 = UmmaCfg<64, 2, 2>;   // 48 KB / stage, 2 CTAs per SM
+using U128 = UmmaCfg<128, 3, 1, 8>;   // 64 KB / stage, 1 CTA per SM, 8 producer warps
+using U256 = UmmaCfg<256, 2, 1, 8>;   // 96 KB / stage, 1 CTA per SM, 8 producer warps
+// the same with a B-loader warp, for GEMMs whose B operand is a pre-tiled weight image
+using U64L = UmmaCfg<64, 2, 2, 4, 1>;
+using U128L = UmmaCfg<128, 3, 1, 8, 1>;
+using U256L = UmmaCfg<256, 2, 1, 8, 1>;
+
+// math mode 3 (experimental): the persistent, fully warp-specialised variant of each tensor-core configuration
+template <class U> struct PersistOf;
+template <> struct PersistOf<U32> { using type = UmmaPCfg<32, 5, 8>; };
+template <> struct PersistOf<U64> { using type = UmmaPCfg<64, 4, 8>; };
+template <> struct PersistOf<U128> { using type = UmmaPCfg<128, 3, 8>; };
+template <> struct PersistOf<U256> { using type = UmmaPCfg<256, 2, 8>; };
+template <> struct PersistOf<U64L> { using type = UmmaPCfg<64, 4, 8>; };
+template <> struct PersistOf<U128L> { using type = UmmaPCfg<128, 3, 8>; };
+template <> struct PersistOf<U256L> { using type = UmmaPCfg<256, 2, 8>; };
+
+
+// name the launch for the per-kernel profile, run it on the selected core, count it
+#define GEMM(name, SCfg, UCfg, ...)                          \
+  do {                                                       \
+    prof_mark(s, name);                                      \
+    if (mode == 3) {                                         \
+      DRL_TRY((launch_gemm_umma_persist<typename PersistOf<UCfg>::type>(s, __VA_ARGS__))); \
+    } else if (mode == 2) {                                  \
+      DRL_TRY((launch_gemm_umma<UCfg>(s, __VA_ARGS__)));     \
+    } else {                                                 \
+      DRL_TRY((launch_gemm_simt<SCfg>(s, __VA_ARGS__)));     \
+    }                                                        \
+    ++n;                                                     \
+  } while (0)
+// same, for GEMMs whose B operand is a weight matrix: the tensor-core cores read its pre-tiled image (blp)
+#define GEMM_W(name, SCfg, UCfg, al, bl, blp, ...)            \
+  do {                                                       \
+    prof_mark(s, name);                                      \
+    if (mode == 3) {                                         \
+      DRL_TRY((launch_gemm_umma_persist<typename PersistOf<UCfg>::type>(s, al, blp, __VA_ARGS__))); \
+    } else if (mode == 2) {                                  \
+      DRL_TRY((launch_gemm_umma<UCfg>(s, al, blp, __VA_ARGS__))); \
+    } else {                                                 \
+      DRL_TRY((launch_gemm_simt<SCfg>(s, al, bl, __VA_ARGS__))); \
+    }                                                        \
+    ++n;                                                     \
+  } while (0)
+#define GEMM_FFMA(name, SCfg, ...)                           \
+  do {                                                       \
+    prof_mark(s, name);                                      \
+    DRL_TRY((launch_gemm_simt<SCfg>(s, __VA_ARGS__)));       \
+    ++n;                                                     \
+  } while (0)
+#define KERNEL(name, call, cnt)                              \
+  do {                                                       \
+    prof_mark(s, name);                                      \
+    DRL_TRY(call);                                           \
+    n += (cnt);                                              \
+  } while (0)
+
+// split-K plan: about `waves` waves of CTAs on 148 SMs
+struct SplitPlan { int splits, kchunk; };
+static SplitPlan plan_split(int K, int tiles_mn, int bk, int waves) {
+  int target = (waves * 148 + tiles_mn - 1) / tiles_mn;
+  if (target < 1) target = 1;
+  int kchunk = (K + target - 1) / target;
+  kchunk = (kchunk + bk - 1) / bk * bk;
+  if (kchunk < bk) kchunk = bk;
+  SplitPlan p;
+  p.kchunk = kchunk;
+  p.splits = (K + kchunk - 1) / kchunk;
+  return p;
+}
+// the conv weight-gradient plans (mode 1: FFMA tiles, 2 waves; mode 2: 128-row UMMA tiles, 2 CTAs/SM)
+static SplitPlan plan_conv1_wgrad(int Mb, int mode) {
+  return mode >= 2 ? plan_split(Mb * 400, 2, 32, 2) : plan_split(Mb * 400, cdiv(256, CfgWg1::BM), 16, 2);
+}
+static SplitPlan plan_conv2_wgrad(int Mb, int mode) {
+  return mode >= 2 ? plan_split(Mb * 81, 4, 32, 2) : plan_split(Mb * 81, cdiv(512, CfgBig::BM), 16, 2);
+}
+static SplitPlan plan_conv3_wgrad(int Mb, int mode) {
+  return mode >= 2 ? plan_split(Mb * 49, 5, 32, 2) : plan_split(Mb * 49, cdiv(576, CfgBig::BM), 16, 2);
+}
+
+}  // namespace drl

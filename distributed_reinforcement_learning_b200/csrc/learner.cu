@@ -65,6 +65,36 @@ void prof_mark(cudaStream_t s, const char* name) {
   g_prof.names.push_back(name);
 }
 
+void prof_begin() {
+  g_prof.on = true;
+  g_prof.ev.clear();
+  g_prof.names.clear();
+}
+int prof_end(cudaStream_t s, int rc, char* names, int64_t names_len, float* ms, int32_t max_kernels, int32_t* count) {
+  g_prof.on = false;
+  cudaError_t e = cudaStreamSynchronize(s);
+  int n = 0;
+  std::string joined;
+  if (rc == DRL_OK && e == cudaSuccess) {
+    for (size_t i = 0; i + 1 < g_prof.ev.size() && n < max_kernels; ++i) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, g_prof.ev[i], g_prof.ev[i + 1]);
+      ms[n++] = t;
+      if (!joined.empty()) joined += "\n";
+      joined += g_prof.names[i];
+    }
+  }
+  for (cudaEvent_t ev : g_prof.ev) cudaEventDestroy(ev);
+  g_prof.ev.clear();
+  g_prof.names.clear();
+  if (rc != DRL_OK) return rc;
+  if (e != cudaSuccess) { set_error("profile step failed: %s", cudaGetErrorString(e)); return DRL_ERR_CUDA; }
+  if ((int64_t)joined.size() + 1 > names_len) { set_error("profile: names buffer too small"); return DRL_ERR_INVALID; }
+  memcpy(names, joined.c_str(), joined.size() + 1);
+  *count = n;
+  return DRL_OK;
+}
+
 struct Slot {
   uint8_t* base = nullptr;   // one allocation, fields at 256-byte aligned offsets
   Inputs in{};
@@ -855,35 +885,13 @@ int drl_learner_profile_step(drl_learner* h, int32_t slot, char* names, int64_t 
   if (!sl.has_data) { set_error("slot %d has not been staged", slot); return DRL_ERR_STATE; }
   DRL_CUDA_CHECK(cudaStreamWaitEvent(h->compute, sl.staged, 0));
   DRL_CUDA_CHECK(cudaStreamSynchronize(h->compute));
-  g_prof.on = true;
-  g_prof.ev.clear();
-  g_prof.names.clear();
+  prof_begin();
   const bool par_saved = h->par;
   h->par = false;                       // serial: the event-to-event times are then per kernel
   int rc = enqueue_forward_backward(h, slot);
   if (rc == DRL_OK) rc = enqueue_apply(h, (int)h->slots.size(), /*local_only=*/true);   // one rank may profile alone
   h->par = par_saved;
-  g_prof.on = false;
-  cudaError_t e = cudaStreamSynchronize(h->compute);
-  int n = 0;
-  std::string joined;
-  if (rc == DRL_OK && e == cudaSuccess) {
-    for (size_t i = 0; i + 1 < g_prof.ev.size() && n < max_kernels; ++i) {
-      float t = 0.f;
-      cudaEventElapsedTime(&t, g_prof.ev[i], g_prof.ev[i + 1]);
-      ms[n++] = t;
-      if (!joined.empty()) joined += "\n";
-      joined += g_prof.names[i];
-    }
-  }
-  for (cudaEvent_t ev : g_prof.ev) cudaEventDestroy(ev);
-  g_prof.ev.clear();
-  g_prof.names.clear();
-  if (rc != DRL_OK) return rc;
-  if (e != cudaSuccess) { set_error("profile step failed: %s", cudaGetErrorString(e)); return DRL_ERR_CUDA; }
-  if ((int64_t)joined.size() + 1 > names_len) { set_error("profile: names buffer too small"); return DRL_ERR_INVALID; }
-  memcpy(names, joined.c_str(), joined.size() + 1);
-  *count = n;
+  DRL_TRY(prof_end(h->compute, rc, names, names_len, ms, max_kernels, count));
   h->pending = false;
   return DRL_OK;
 }

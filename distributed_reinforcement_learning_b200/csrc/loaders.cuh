@@ -224,6 +224,93 @@ struct LstmAT {  // transposed view for dW = X^T dz : index i = feature (contigu
 };
 
 // --------------------------------------------------------------------------------------------
+// Ape-X dueling network operands (model/apex_value.py:22-41): both streams read
+// concat_m = [flatten(a3_m) | emb[previous_action_m]] (K = 3392); rows are already in caller order.
+// --------------------------------------------------------------------------------------------
+struct CatA {    // K-contiguous rows
+  static constexpr bool kContigK = true;
+  const float* e;       // [M, 3136]
+  const float* table;   // [A, 256]
+  const int* pa;        // [M]
+  struct Row { const float *pe, *pu; };
+  __device__ __forceinline__ Row row(int, int m) const {
+    Row r;
+    if (m < 0) { r.pe = nullptr; r.pu = nullptr; return r; }
+    r.pe = e + (size_t)m * Geo::FLAT;
+    r.pu = table + (size_t)__ldg(pa + m) * Geo::EMB;
+    return r;
+  }
+  __device__ __forceinline__ float4 load(const Row& r, int k) const {
+    if (r.pe == nullptr) return zero4();
+    return __ldg(reinterpret_cast<const float4*>((k < Geo::FLAT) ? r.pe + k : r.pu + (k - Geo::FLAT)));
+  }
+};
+struct CatAT {   // transposed view for dW1 = concat^T dhid1 : index i = feature (contiguous), reduction r = row
+  static constexpr bool kContigK = false;
+  const float* e;
+  const float* table;
+  const int* pa;
+  struct Row { int i; };
+  __device__ __forceinline__ Row row(int, int i) const { Row r; r.i = i; return r; }
+  __device__ __forceinline__ float4 load(const Row& r, int m) const {
+    if (r.i < 0) return zero4();
+    const float* p = (r.i < Geo::FLAT) ? e + (size_t)m * Geo::FLAT + r.i
+                                       : table + (size_t)__ldg(pa + m) * Geo::EMB + (r.i - Geo::FLAT);
+    return __ldg(reinterpret_cast<const float4*>(p));
+  }
+};
+// Two matrices side by side along N (B(k, n) = n < n0 ? b0[k][n] : b1[k][n - n0]), N-contiguous: the first layers
+// of the value and the "mean" stream evaluated by ONE GEMM with N = 2 * 256.
+struct DualB {
+  static constexpr bool kContigK = false;
+  const float* b0; const float* b1; int ldb; int n0;
+  struct Row { const float* p; };
+  __device__ __forceinline__ Row row(int, int n) const {
+    Row r;
+    r.p = n < 0 ? nullptr : (n < n0 ? b0 + n : b1 + (n - n0));
+    return r;
+  }
+  __device__ __forceinline__ float4 load(const Row& r, int k) const {
+    return r.p ? __ldg(reinterpret_cast<const float4*>(r.p + (size_t)k * ldb)) : zero4();
+  }
+};
+// Two matrices side by side along K: A(m, k) = k < k0 ? a0[m][k] : a1[m][k - k0], K-contiguous, and the matching
+// B(k, n) = k < k0 ? w0[n][k] : w1[n][k - k0] (transposed weights): d concat = dhid1_value W1v^T + dhid1_mean W1m^T
+// as ONE GEMM with K = 2 * 256.
+struct DualA {
+  static constexpr bool kContigK = true;
+  const float* a0; const float* a1; int lda; int k0;
+  struct Row { const float *p0, *p1; };
+  __device__ __forceinline__ Row row(int, int m) const {
+    Row r;
+    if (m < 0) { r.p0 = nullptr; r.p1 = nullptr; return r; }
+    r.p0 = a0 + (size_t)m * lda;
+    r.p1 = a1 + (size_t)m * lda;
+    return r;
+  }
+  __device__ __forceinline__ float4 load(const Row& r, int k) const {
+    if (r.p0 == nullptr) return zero4();
+    return __ldg(reinterpret_cast<const float4*>(k < k0 ? r.p0 + k : r.p1 + (k - k0)));
+  }
+};
+struct DualBT {
+  static constexpr bool kContigK = true;
+  const float* w0; const float* w1; int ldb; int k0;
+  struct Row { const float *p0, *p1; };
+  __device__ __forceinline__ Row row(int, int n) const {
+    Row r;
+    if (n < 0) { r.p0 = nullptr; r.p1 = nullptr; return r; }
+    r.p0 = w0 + (size_t)n * ldb;
+    r.p1 = w1 + (size_t)n * ldb;
+    return r;
+  }
+  __device__ __forceinline__ float4 load(const Row& r, int k) const {
+    if (r.p0 == nullptr) return zero4();
+    return __ldg(reinterpret_cast<const float4*>(k < k0 ? r.p0 + k : r.p1 + (k - k0)));
+  }
+};
+
+// --------------------------------------------------------------------------------------------
 // Plain strided operands (z = batch index with element strides sz).
 // --------------------------------------------------------------------------------------------
 struct PlainA {    // A[z][m][k], K-contiguous

@@ -1,4 +1,5 @@
-"""B200-native stand-in for ``distributed_queue/buffer_queue.py::FIFOQueue`` (reference :418-512).
+"""B200-native stand-ins for ``distributed_queue/buffer_queue.py``: ``FIFOQueue`` (reference :418-512, the IMPALA
+trajectory queue) and ``SumTree`` / ``Memory`` (reference :326-416, the Ape-X prioritized replay memory).
 
 The reference keeps a ``tf.FIFOQueue`` of 9-field trajectories on the learner's CPU and dequeues a
 batch with ``batch_size`` serial ``sess.run`` RPCs, after which the launcher ``np.stack``s eight
@@ -103,3 +104,85 @@ class FIFOQueue:
     def set_session(self, sess):
         """buffer_queue.py:511-512 (kept for call compatibility; there is no session)."""
         self.sess = sess
+
+
+class SumTree:
+    """buffer_queue.py:326-369 over the native float64 sum tree (``drl_per_*``): same attributes and methods; the
+    stored objects stay in a host list, the priorities live in the native tree."""
+
+    def __init__(self, capacity):
+        self.capacity = int(capacity)
+        self.data = np.zeros(self.capacity, dtype=object)
+        self._p = C.c_void_p()
+        N.check(N.lib.drl_per_create(self.capacity, C.byref(self._p)))
+
+    def close(self):
+        if getattr(self, "_p", None) is not None and self._p.value:
+            N.lib.drl_per_destroy(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def n_entries(self):
+        n = C.c_int64()
+        N.check(N.lib.drl_per_size(self._p, C.byref(n)))
+        return int(n.value)
+
+    def total(self):
+        t = C.c_double()
+        N.check(N.lib.drl_per_total(self._p, C.byref(t)))
+        return float(t.value)
+
+
+class Memory(object):
+    """buffer_queue.py:371-415: prioritized replay with p = (|td| + 0.001) ** 0.6, stratified sampling and importance
+    weights (n_entries * p / total) ** -beta / max, beta 0.4 -> 1 by +0.001 per ``sample`` call."""
+    e = 0.001
+    a = 0.6
+    beta_increment_per_sampling = 0.001
+
+    def __init__(self, capacity):
+        self.capacity = capacity
+        self.tree = SumTree(capacity)
+
+    def reset(self):
+        self.tree.close()
+        self.tree = SumTree(self.capacity)
+
+    @property
+    def beta(self):
+        b = C.c_double()
+        N.check(N.lib.drl_per_beta(self.tree._p, C.byref(b)))
+        return float(b.value)
+
+    def _getPriority(self, error):
+        return (error + self.e) ** self.a
+
+    def add(self, error, sample):
+        idx = C.c_int64()
+        N.check(N.lib.drl_per_add(self.tree._p, float(error), C.byref(idx)))
+        self.tree.data[idx.value] = sample
+
+    def sample(self, n, u01=None):
+        """-> (batch, idxs, is_weight) like the reference; ``u01`` ([n] uniforms in [0, 1)) makes the draw
+        reproducible, by default they come from ``random.random`` as in the reference."""
+        if u01 is None:
+            import random
+            u01 = [random.random() for _ in range(n)]
+        u = N.as_c(u01, np.float64, (n,), "u01")
+        ti = np.empty(n, np.int64)
+        di = np.empty(n, np.int64)
+        pr = np.empty(n, np.float64)
+        w = np.empty(n, np.float64)
+        N.check(N.lib.drl_per_sample(self.tree._p, n, N.ptr(u), N.ptr(ti), N.ptr(di), N.ptr(pr), N.ptr(w)))
+        batch = [self.tree.data[i] for i in di]
+        self.last_priorities = pr
+        return batch, [int(i) for i in ti], w
+
+    def update(self, idx, error):
+        N.check(N.lib.drl_per_update(self.tree._p, int(idx), float(error)))

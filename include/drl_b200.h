@@ -256,6 +256,119 @@ int drl_ring_release(drl_ring* r, int32_t slot);
 /* FIFOQueue.get_size (buffer_queue.py:507-509): trajectories enqueued and not yet popped. */
 int drl_ring_size(drl_ring* r);
 
+/* ------------------------------------------------------------------------------------------
+ * Ape-X DQN learner (BASELINE.json config 4): replaces apex.Agent's learner graph
+ * (agent/apex.py:12-76) over model/apex_value.py:4-66 (dueling network: q = value stream - "mean" stream, evaluated
+ * as main(s, prev_a), main(s', a), target(s', a)), optimizer/dqn.py:3-7 and TF1 Adam.  The three network
+ * evaluations run as ONE main-network forward over 2B rows [s ; s'] plus one target-network forward over B rows;
+ * only the first B rows are differentiated.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct drl_apex drl_apex;
+
+#define DRL_APEX_MAIN 0
+#define DRL_APEX_TARGET 1
+
+typedef struct drl_apex_config {
+  int32_t batch;              /* B transitions per step (config.json:154)                               */
+  int32_t height, width, channels; /* 84,84,4 -- only this geometry is supported (config.json:156)      */
+  int32_t num_action;         /* A, 2..32 (config.json:157)                                             */
+  float discount_factor;      /* agent/apex.py:43                                                       */
+  float start_learning_rate;  /* agent/apex.py:71                                                       */
+  float end_learning_rate;
+  double learning_frame;      /* decay_steps of tf.train.polynomial_decay                               */
+  float gradient_clip_norm;   /* agent/apex.py:74                                                       */
+  int32_t reward_clipping;    /* DRL_REWARD_ABS_ONE clips to [-1,1]; anything else passes the reward through
+                                 (agent/apex.py:38-41)                                                  */
+  int32_t device;             /* CUDA device ordinal                                                    */
+  int32_t num_slots;          /* device staging slots for stream-overlapped H2D (>=1, default 2)        */
+  int32_t use_cuda_graph;     /* 1: capture the whole step into one CUDA graph per slot                 */
+  int32_t math_mode;          /* 0 = default (2); 1 = FP32 FFMA; 2 = tcgen05 3xTF32 convolutions        */
+} drl_apex_config;
+
+typedef struct drl_apex_out {
+  float loss;           /* value_loss = mean(is_weight * (target_value - state_action_value)^2), agent/apex.py:63-65 */
+  float learning_rate;  /* agent/apex.py:71 */
+  float grad_norm;      /* global norm before clipping (agent/apex.py:74) */
+  int64_t step;         /* global_step AFTER this update (agent/apex.py:70,75) */
+} drl_apex_out;
+
+/* apex.Agent.__init__ (agent/apex.py:12-76): parameters of 'main' and 'target' (zeros until set), Adam slots m, v
+ * (zeros), beta powers (0.9, 0.999), activations, staging slots, streams on cfg->device. */
+int drl_apex_create(const drl_apex_config* cfg, drl_apex** out);
+int drl_apex_destroy(drl_apex* h);
+/* Learnable floats of ONE network (main and target have the same inventory). */
+int drl_apex_param_count(const drl_apex* h, int64_t* n);
+/* Flat float32 vector in TF layouts / TF variable-creation order of the scope ({model}/main or {model}/target):
+ * conv2d x3 (HWIO), dense x2 (action embedding), dense x3 (value stream), dense x3 ("mean" stream); which =
+ * DRL_APEX_MAIN / DRL_APEX_TARGET.  Replaces global_variables_initializer / Saver (agent/apex.py:76,84-86). */
+int drl_apex_set_params(drl_apex* h, int32_t which, const float* host_flat, int64_t n);
+int drl_apex_get_params(drl_apex* h, int32_t which, float* host_flat, int64_t n);
+/* Adam slots of the main network, global_step, beta1_power, beta2_power (agent/apex.py:72). */
+int drl_apex_set_opt_state(drl_apex* h, const float* host_m, const float* host_v, int64_t n, int64_t step,
+                           float beta1_power, float beta2_power);
+int drl_apex_get_opt_state(drl_apex* h, float* host_m, float* host_v, int64_t n, int64_t* step,
+                           float* beta1_power, float* beta2_power);
+/* Gradient of value_loss w.r.t. the main network, before clipping (parity tap of compute_gradients, agent/apex.py:73). */
+int drl_apex_get_grads(drl_apex* h, float* host_flat, int64_t n);
+/* Agent.target_to_main (agent/apex.py:78-79 -> utils.main_to_target, utils.py:27-32): despite its name it assigns
+ * target <- main. */
+int drl_apex_target_to_main(drl_apex* h);
+
+/* Feed of Agent.distributed_train (agent/apex.py:135-149): asynchronous H2D into staging slot `slot`.
+ * state, next_state u8 [B,H,W,C] (the /255 of :136-137 happens on the device); previous_action, action i32 [B];
+ * reward f32 [B]; done u8/bool [B]; is_weight f32 [B] or NULL (= ones: Agent.train, agent/apex.py:156-168). */
+int drl_apex_stage(drl_apex* h, int32_t slot, const uint8_t* state, const uint8_t* next_state,
+                   const int32_t* previous_action, const int32_t* action, const float* reward,
+                   const uint8_t* done, const float* is_weight);
+/* sess.run([value_loss, target_value, state_action_value, train_op]) (agent/apex.py:139-149): forward x3, TD target,
+ * weighted squared loss, backward through main(s), global-norm clip, Adam, step += 1.  td_error (host, [B], may be
+ * NULL) receives |target_value - state_action_value| from BEFORE the update (agent/apex.py:151): the new priorities. */
+int drl_apex_step(drl_apex* h, int32_t slot, drl_apex_out* out, float* td_error);
+int drl_apex_step_async(drl_apex* h, int32_t slot);
+int drl_apex_wait(drl_apex* h, drl_apex_out* out, float* td_error);
+/* Agent.get_td_error (agent/apex.py:116-133): forward only, n <= batch transitions -> |target - q(s,a)| [n]. */
+int drl_apex_td_error(drl_apex* h, int32_t n, const uint8_t* state, const uint8_t* next_state,
+                      const int32_t* previous_action, const int32_t* action, const float* reward,
+                      const uint8_t* done, float* td_error);
+/* Agent.get_policy_and_action without the epsilon-greedy draw (agent/apex.py:88-102): main_q_value [n, A] for
+ * n <= 2*batch (state, previous_action) pairs. */
+int drl_apex_act(drl_apex* h, int32_t n, const uint8_t* state, const int32_t* previous_action, float* q_value);
+/* Parity taps of the most recent step / td_error call over its n rows (agent/apex.py:45-61): main_q_value,
+ * next_main_q_value, target_q_value [n, A]; target_value, state_action_value [n].  Any pointer may be NULL. */
+int drl_apex_taps(drl_apex* h, float* main_q, float* next_main_q, float* target_q, float* target_value,
+                  float* state_action_value);
+/* Debug/parity: copy a named device buffer of the MAIN network's last forward to the host.  Names: a1 a2 a3 e1 emb
+ * hid1 hid2 (rows = 2n: [s ; s']), da1 da2 da3 (rows = n). */
+int drl_apex_read_buffer(drl_apex* h, const char* name, float* host_dst, int64_t n);
+/* Per-launch device times of one real step (CUDA events around every launch, serial). */
+int drl_apex_profile_step(drl_apex* h, int32_t slot, char* names, int64_t names_len, float* ms, int32_t max_kernels,
+                          int32_t* count);
+int drl_apex_last_step_ms(drl_apex* h, float* ms);
+int drl_apex_launches_per_step(const drl_apex* h, int32_t* n);
+
+/* ------------------------------------------------------------------------------------------
+ * Prioritized replay index (host): replaces buffer_queue.SumTree / Memory (distributed_queue/buffer_queue.py:326-416)
+ * -- float64 sum tree with the reference's arithmetic order (bit-identical totals), priorities (|td| + 0.001)^0.6,
+ * stratified sampling, importance weights (n_entries * p / total)^-beta / max, beta 0.4 -> 1 by +0.001 per sample
+ * call.  The transitions themselves stay with the caller (the Python shim keeps them, as the reference does); the
+ * uniform draws of random.uniform(a, b) are passed in as u01 in [0,1) so that sampling is reproducible.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct drl_per drl_per;
+int drl_per_create(int64_t capacity, drl_per** out);
+int drl_per_destroy(drl_per* p);
+/* Memory.add (buffer_queue.py:386-388): stores priority (error + e)^a at the write cursor; returns the data index
+ * the caller must store the transition at (SumTree.add, :351-359). */
+int drl_per_add(drl_per* p, double error, int64_t* data_index);
+/* Memory.sample (buffer_queue.py:390-411): n strata; tree_index[i] (SumTree.get's idx), data_index[i],
+ * priority[i], is_weight[i]; also advances beta. */
+int drl_per_sample(drl_per* p, int32_t n, const double* u01, int64_t* tree_index, int64_t* data_index,
+                   double* priority, double* is_weight);
+/* Memory.update (buffer_queue.py:413-415): tree_index as returned by drl_per_sample. */
+int drl_per_update(drl_per* p, int64_t tree_index, double error);
+int drl_per_total(const drl_per* p, double* total);      /* SumTree.total (:348-349) */
+int drl_per_size(const drl_per* p, int64_t* n_entries);  /* SumTree.n_entries */
+int drl_per_beta(const drl_per* p, double* beta);
+
 #ifdef __cplusplus
 }
 #endif
