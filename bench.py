@@ -494,7 +494,15 @@ def main():
     ap.add_argument("--collective", choices=["peer", "nccl", "none"], default="peer",
                     help="N > 1: fused peer-memory gradient exchange (default) or NCCL all_reduce; 'none' = no "
                          "exchange at all (diagnostic: N independent replicas, NOT a valid data-parallel step)")
+    ap.add_argument("--workload", choices=["impala", "apex"], default="impala",
+                    help="impala = the headline IMPALA learner step (default); apex = the Ape-X DQN learner step "
+                         "(BASELINE configs[3], tools/bench_apex.py)")
     args = ap.parse_args()
+    if args.workload == "apex":
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_apex
+        bench_apex.run(args, sys.modules[__name__])
+        return
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -131,6 +131,7 @@ def _load():
         "drl_apex_profile_step": (C.c_int, [vp, i32, C.c_char_p, i64, vp, i32, C.POINTER(i32)]),
         "drl_apex_last_step_ms": (C.c_int, [vp, C.POINTER(f32)]),
         "drl_apex_launches_per_step": (C.c_int, [vp, C.POINTER(i32)]),
+        "drl_apex_stream": (C.c_int, [vp, C.POINTER(vp)]),
         "drl_per_create": (C.c_int, [i64, C.POINTER(vp)]),
         "drl_per_destroy": (C.c_int, [vp]),
         "drl_per_add": (C.c_int, [vp, C.c_double, C.POINTER(i64)]),

@@ -168,3 +168,8 @@ class NativeApexLearner:
         n = C.c_int32()
         N.check(N.lib.drl_apex_launches_per_step(self._h, C.byref(n)))
         return int(n.value)
+
+    def stream_ptr(self):
+        s = C.c_void_p()
+        N.check(N.lib.drl_apex_stream(self._h, C.byref(s)))
+        return int(s.value or 0)

@@ -1109,6 +1109,13 @@ int drl_apex_last_step_ms(drl_apex* h, float* ms) {
   return DRL_OK;
 }
 
+int drl_apex_stream(drl_apex* h, void** stream) {
+  DRL_TRY(check_handle(h));
+  if (!stream) { set_error("null argument"); return DRL_ERR_INVALID; }
+  *stream = h->compute;
+  return DRL_OK;
+}
+
 int drl_apex_launches_per_step(const drl_apex* h, int32_t* n) {
   DRL_TRY(check_handle(h));
   if (!n) { set_error("null argument"); return DRL_ERR_INVALID; }

@@ -344,6 +344,8 @@ int drl_apex_read_buffer(drl_apex* h, const char* name, float* host_dst, int64_t
 int drl_apex_profile_step(drl_apex* h, int32_t slot, char* names, int64_t names_len, float* ms, int32_t max_kernels,
                           int32_t* count);
 int drl_apex_last_step_ms(drl_apex* h, float* ms);
+/* The learner's compute stream (cudaStream_t), for callers that time or order work against it. */
+int drl_apex_stream(drl_apex* h, void** stream);
 int drl_apex_launches_per_step(const drl_apex* h, int32_t* n);
 
 /* ------------------------------------------------------------------------------------------
