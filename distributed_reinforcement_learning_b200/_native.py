@@ -53,6 +53,17 @@ class ApexOut(C.Structure):
     _fields_ = [("loss", C.c_float), ("learning_rate", C.c_float), ("grad_norm", C.c_float), ("step", C.c_int64)]
 
 
+class R2d2Config(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("seq_len", C.c_int32), ("burn_in", C.c_int32), ("height", C.c_int32),
+                ("width", C.c_int32), ("channels", C.c_int32), ("num_action", C.c_int32), ("lstm_size", C.c_int32),
+                ("discount_factor", C.c_float), ("learning_rate", C.c_float), ("device", C.c_int32),
+                ("num_slots", C.c_int32), ("use_cuda_graph", C.c_int32), ("math_mode", C.c_int32)]
+
+
+class R2d2Out(C.Structure):
+    _fields_ = [("loss", C.c_float), ("grad_norm", C.c_float), ("step", C.c_int64)]
+
+
 class RingBatch(C.Structure):
     _fields_ = [("state", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p),
                 ("behavior_policy", C.c_void_p), ("action", C.c_void_p), ("previous_action", C.c_void_p),
@@ -132,6 +143,27 @@ def _load():
         "drl_apex_last_step_ms": (C.c_int, [vp, C.POINTER(f32)]),
         "drl_apex_launches_per_step": (C.c_int, [vp, C.POINTER(i32)]),
         "drl_apex_stream": (C.c_int, [vp, C.POINTER(vp)]),
+        "drl_r2d2_create": (C.c_int, [C.POINTER(R2d2Config), C.POINTER(vp)]),
+        "drl_r2d2_destroy": (C.c_int, [vp]),
+        "drl_r2d2_param_count": (C.c_int, [vp, C.POINTER(i64)]),
+        "drl_r2d2_set_params": (C.c_int, [vp, i32, vp, i64]),
+        "drl_r2d2_get_params": (C.c_int, [vp, i32, vp, i64]),
+        "drl_r2d2_set_opt_state": (C.c_int, [vp, vp, vp, i64, i64, f32, f32]),
+        "drl_r2d2_get_opt_state": (C.c_int, [vp, vp, vp, i64, C.POINTER(i64), C.POINTER(f32), C.POINTER(f32)]),
+        "drl_r2d2_get_grads": (C.c_int, [vp, vp, i64]),
+        "drl_r2d2_main_to_target": (C.c_int, [vp]),
+        "drl_r2d2_stage": (C.c_int, [vp, i32] + [vp] * 8),
+        "drl_r2d2_step": (C.c_int, [vp, i32, C.POINTER(R2d2Out), vp]),
+        "drl_r2d2_step_async": (C.c_int, [vp, i32]),
+        "drl_r2d2_wait": (C.c_int, [vp, C.POINTER(R2d2Out), vp]),
+        "drl_r2d2_td_error": (C.c_int, [vp, i32] + [vp] * 8),
+        "drl_r2d2_act": (C.c_int, [vp, i32] + [vp] * 7),
+        "drl_r2d2_taps": (C.c_int, [vp] * 5),
+        "drl_r2d2_read_buffer": (C.c_int, [vp, C.c_char_p, vp, i64]),
+        "drl_r2d2_profile_step": (C.c_int, [vp, i32, C.c_char_p, i64, vp, i32, C.POINTER(i32)]),
+        "drl_r2d2_last_step_ms": (C.c_int, [vp, C.POINTER(f32)]),
+        "drl_r2d2_stream": (C.c_int, [vp, C.POINTER(vp)]),
+        "drl_r2d2_launches_per_step": (C.c_int, [vp, C.POINTER(i32)]),
         "drl_per_create": (C.c_int, [i64, C.POINTER(vp)]),
         "drl_per_destroy": (C.c_int, [vp]),
         "drl_per_add": (C.c_int, [vp, C.c_double, C.POINTER(i64)]),

@@ -178,14 +178,6 @@ __global__ void __launch_bounds__(256) apex_td_kernel(TdArgs a) {
 //   beta powers *= beta ; global_step += 1
 // Two launches: (1) partial squared norms + the scalars, (2) every block re-reduces the partials in fixed order.
 // ------------------------------------------------------------------------------------------
-struct AdamState {
-  float* params; float* m; float* v; const float* grads; int64_t n;
-  float* norm_partials; int nblk;
-  long long* step; float* lr_cur; float* alpha; float* b1p; float* b2p;
-  float* out;               // [8] mapped pinned: loss, lr, grad_norm, -, -, -, step_lo, step_hi
-  const float* loss;
-  float start_lr, end_lr; double learning_frame; float clip_norm;
-};
 constexpr float kBeta1 = 0.9f, kBeta2 = 0.999f, kAdamEps = 1e-8f;
 
 __global__ void __launch_bounds__(256) adam_prepare_kernel(AdamState o) {
@@ -236,7 +228,7 @@ __global__ void __launch_bounds__(256) adam_apply_kernel(AdamState o) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) s += red[i];
     const float norm = sqrtf(s);
-    s_scale = o.clip_norm * fminf(1.0f / norm, 1.0f / o.clip_norm);
+    s_scale = (o.clip_norm > 0.f) ? o.clip_norm * fminf(1.0f / norm, 1.0f / o.clip_norm) : 1.0f;
     if (blockIdx.x == 0) {
       o.out[0] = *o.loss; o.out[1] = *o.lr_cur; o.out[2] = norm;
       const long long st = *o.step;
@@ -262,6 +254,12 @@ __global__ void __launch_bounds__(256) adam_apply_kernel(AdamState o) {
     gg = g.w * scale; m.w += (gg - m.w) * (1.0f - kBeta1); v.w += (gg * gg - v.w) * (1.0f - kBeta2); w.w -= (m.w * alpha) / (sqrtf(v.w) + kAdamEps);
     m4[i] = m; v4[i] = v; w4[i] = w;
   }
+}
+
+int adam_step(cudaStream_t s, const AdamState& o) {
+  DRL_CUDA_CHECK((launch_k(adam_prepare_kernel, o.nblk, 256, 0, s, o)));
+  DRL_CUDA_CHECK((launch_k(adam_apply_kernel, o.nblk, 256, 0, s, o)));
+  return DRL_OK;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -639,8 +637,7 @@ int enqueue_step(drl_apex* h, int slot, int* launches) {
   AdamState o = h->opt;
   o.out = h->d_out + 8 * slot;
   prof_mark(h->compute, "optimizer(norm+adam)");
-  DRL_CUDA_CHECK((launch_k(adam_prepare_kernel, o.nblk, 256, 0, h->compute, o)));
-  DRL_CUDA_CHECK((launch_k(adam_apply_kernel, o.nblk, 256, 0, h->compute, o)));
+  DRL_TRY(adam_step(h->compute, o));
   prof_mark(h->compute, "end");
   if (launches) *launches += 2;
   return DRL_OK;

@@ -174,6 +174,18 @@ struct OptState {
 int optimizer_apply(cudaStream_t s, const OptState& o);
 int optimizer_update_only(cudaStream_t s, const OptState& o);   // clip + RMSProp from already reduced partials
 
+// ---- apex.cu: TF1 Adam (shared by the Ape-X and the R2D2 learner) -------------------------------------------------
+// clip_norm <= 0: no clipping (optimizer.minimize, agent/r2d2.py:92); start_lr == end_lr: constant learning rate
+struct AdamState {
+  float* params; float* m; float* v; const float* grads; int64_t n;
+  float* norm_partials; int nblk;
+  long long* step; float* lr_cur; float* alpha; float* b1p; float* b2p;
+  float* out;               // [8] mapped pinned: loss, lr, grad_norm, -, -, -, step_lo, step_hi
+  const float* loss;
+  float start_lr, end_lr; double learning_frame; float clip_norm;
+};
+int adam_step(cudaStream_t s, const AdamState& o);   // 2 launches: partial norms + scalars, then the update
+
 // ---- peer.cu: gradient exchange over NVLink peer memory (CUDA IPC), fused with the norm ------------------------
 constexpr int kMaxPeers = 16;
 constexpr int kPeerParts = 1;      // exchange instances per step (the kernel takes a sub-range: see DESIGN.md section 5)

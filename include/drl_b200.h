@@ -371,6 +371,84 @@ int drl_per_total(const drl_per* p, double* total);      /* SumTree.total (:348-
 int drl_per_size(const drl_per* p, int64_t* n_entries);  /* SumTree.n_entries */
 int drl_per_beta(const drl_per* p, double* beta);
 
+/* ------------------------------------------------------------------------------------------
+ * R2D2 learner (BASELINE.json config 5): replaces r2d2.Agent's learner graph
+ * (agent/r2d2.py:13-95) over model/r2d2_lstm.py:28-116 (conv stack + action embedding + ONE LSTMCell, unrolled seq_len
+ * steps per scope from a stored (h, c) with the carried state multiplied by (1 - done) after every step; dense 128;
+ * q = value - "mean"), optimizer/burn_in.py:23-32 (value-function rescaling, eps 1e-3), double-Q targets over the
+ * post-burn-in window and TF1 Adam(1e-4) without clipping.  Sequences are batch-major [B, S, ...].
+ * ------------------------------------------------------------------------------------------ */
+typedef struct drl_r2d2 drl_r2d2;
+
+typedef struct drl_r2d2_config {
+  int32_t batch;              /* B sequences per step (config.json:94)                                   */
+  int32_t seq_len;            /* S (config.json:95); BASELINE config 5 asks 80                           */
+  int32_t burn_in;            /* loss window starts here (config.json:96), 0 <= burn_in <= S - 2         */
+  int32_t height, width, channels; /* 84, 84, 1 (config.json:91) or 84, 84, 4                            */
+  int32_t num_action;         /* A, 2..32                                                                */
+  int32_t lstm_size;          /* 64 -- only this size is supported (config.json:93)                      */
+  float discount_factor;      /* agent/r2d2.py:62                                                        */
+  float learning_rate;        /* 1e-4 (agent/r2d2.py:91)                                                 */
+  int32_t device;
+  int32_t num_slots;
+  int32_t use_cuda_graph;
+  int32_t math_mode;          /* 0 = default (2); 1 = FP32 FFMA; 2 = tcgen05 3xTF32 for the large contractions */
+} drl_r2d2_config;
+
+typedef struct drl_r2d2_out {
+  float loss;        /* value_loss (agent/r2d2.py:90) */
+  float grad_norm;   /* global gradient norm (diagnostic; the reference does not clip) */
+  int64_t step;      /* updates applied so far */
+} drl_r2d2_out;
+
+int drl_r2d2_create(const drl_r2d2_config* cfg, drl_r2d2** out);
+int drl_r2d2_destroy(drl_r2d2* h);
+int drl_r2d2_param_count(const drl_r2d2* h, int64_t* n);   /* floats of ONE scope */
+/* Flat float32 vector of scope `which` (0 = main, 1 = target) in TF layouts / TF variable-creation order: conv2d x3
+ * (HWIO), dense x2 (action embedding), rnn/lstm_cell kernel [3136+256+L, 4L] (gate order i,j,f,o) + bias, dense 128,
+ * dense A (value), dense 1 (mean). */
+int drl_r2d2_set_params(drl_r2d2* h, int32_t which, const float* host_flat, int64_t n);
+int drl_r2d2_get_params(drl_r2d2* h, int32_t which, float* host_flat, int64_t n);
+int drl_r2d2_set_opt_state(drl_r2d2* h, const float* host_m, const float* host_v, int64_t n, int64_t step,
+                           float beta1_power, float beta2_power);
+int drl_r2d2_get_opt_state(drl_r2d2* h, float* host_m, float* host_v, int64_t n, int64_t* step,
+                           float* beta1_power, float* beta2_power);
+int drl_r2d2_get_grads(drl_r2d2* h, float* host_flat, int64_t n);
+/* Agent.main_to_target (agent/r2d2.py:164-165, utils.py:27-32): target <- main. */
+int drl_r2d2_main_to_target(drl_r2d2* h);
+/* Feed of Agent.train (agent/r2d2.py:132-152): state u8 [B,S,H,W,C]; previous_action, action i32 [B,S]; h0, c0 f32
+ * [B,L] (the reference feeds np.stack(h)[:, 0] of the stored [B,S,L] states); reward f32 [B,S]; done u8/bool [B,S];
+ * weight f32 [B] or NULL (= ones). */
+int drl_r2d2_stage(drl_r2d2* h, int32_t slot, const uint8_t* state, const int32_t* previous_action,
+                   const int32_t* action, const float* h0, const float* c0, const float* reward, const uint8_t* done,
+                   const float* weight);
+/* sess.run([value_loss, target_value, state_action_value, train_op]) (agent/r2d2.py:134-152): both unrolls, TD
+ * targets, loss, BPTT through all S steps of the main scope, Adam.  td_error (host [B], may be NULL) receives
+ * |mean_t(target_value - state_action_value)| per sequence from BEFORE the update (agent/r2d2.py:154-157). */
+int drl_r2d2_step(drl_r2d2* h, int32_t slot, drl_r2d2_out* out, float* td_error);
+int drl_r2d2_step_async(drl_r2d2* h, int32_t slot);
+int drl_r2d2_wait(drl_r2d2* h, drl_r2d2_out* out, float* td_error);
+/* Agent.get_td_error (agent/r2d2.py:97-130) for n <= batch sequences at once: td_error[i] = |mean(target - q)| of
+ * sequence i (the reference calls it with one sequence). */
+int drl_r2d2_td_error(drl_r2d2* h, int32_t n, const uint8_t* state, const int32_t* previous_action,
+                      const int32_t* action, const float* h0, const float* c0, const float* reward,
+                      const uint8_t* done, float* td_error);
+/* Agent.get_action without the epsilon-greedy draw (agent/r2d2.py:171-191): one network step for n <= batch*seq_len
+ * (state, previous_action, h, c) rows -> q_value [n,A], h' [n,L], c' [n,L]. */
+int drl_r2d2_act(drl_r2d2* h, int32_t n, const uint8_t* state, const int32_t* previous_action, const float* h_in,
+                 const float* c_in, float* q_value, float* h_out, float* c_out);
+/* Parity taps of the most recent step / td_error call over its n sequences: main_q, target_q [n,S,A] (agent/r2d2.py:52),
+ * target_value, state_action_value [n, S - burn_in - 1] (:81-88).  Any pointer may be NULL. */
+int drl_r2d2_taps(drl_r2d2* h, float* main_q, float* target_q, float* target_value, float* state_action_value);
+/* Debug/parity: named device buffer of the main scope (time-major rows m = t*n + b): a1 a2 a3 e1 emb q1 hout hin cin
+ * gates dz dhout da3. */
+int drl_r2d2_read_buffer(drl_r2d2* h, const char* name, float* host_dst, int64_t n);
+int drl_r2d2_profile_step(drl_r2d2* h, int32_t slot, char* names, int64_t names_len, float* ms, int32_t max_kernels,
+                          int32_t* count);
+int drl_r2d2_last_step_ms(drl_r2d2* h, float* ms);
+int drl_r2d2_stream(drl_r2d2* h, void** stream);
+int drl_r2d2_launches_per_step(const drl_r2d2* h, int32_t* n);
+
 #ifdef __cplusplus
 }
 #endif
