@@ -494,14 +494,15 @@ def main():
     ap.add_argument("--collective", choices=["peer", "nccl", "none"], default="peer",
                     help="N > 1: fused peer-memory gradient exchange (default) or NCCL all_reduce; 'none' = no "
                          "exchange at all (diagnostic: N independent replicas, NOT a valid data-parallel step)")
-    ap.add_argument("--workload", choices=["impala", "apex"], default="impala",
+    ap.add_argument("--workload", choices=["impala", "apex", "r2d2"], default="impala",
                     help="impala = the headline IMPALA learner step (default); apex = the Ape-X DQN learner step "
-                         "(BASELINE configs[3], tools/bench_apex.py)")
+                         "(BASELINE configs[3], tools/bench_apex.py); r2d2 = the R2D2 learner step (configs[4], "
+                         "tools/bench_r2d2.py)")
     args = ap.parse_args()
-    if args.workload == "apex":
+    if args.workload != "impala":
         sys.path.insert(0, os.path.join(ROOT, "tools"))
-        import bench_apex
-        bench_apex.run(args, sys.modules[__name__])
+        leg = __import__("bench_" + args.workload)
+        leg.run(args, sys.modules[__name__])
         return
     if args.impl == "reference":
         run_reference(args)

@@ -508,6 +508,9 @@ struct drl_apex {
   cudaStream_t compute = nullptr, copy = nullptr, side = nullptr;
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done = nullptr;
   cudaEvent_t fj[8] = {};
+  // the target scope's forward is independent of the main scope's: it runs on its own stream pair beside it
+  cudaStream_t tmain = nullptr, tside = nullptr;
+  cudaEvent_t tfj[8] = {}, ev_tfork = nullptr, ev_tjoin = nullptr;
   bool par = true;
   float *params = nullptr, *target = nullptr, *adam_m = nullptr, *adam_v = nullptr, *grads = nullptr;
   ApexActs act{}, tact{};
@@ -571,6 +574,16 @@ int download_flat(drl_apex* h, const float* dev_padded, float* host_packed) {
   return DRL_OK;
 }
 
+// stream pair of the target scope: its own pair when the step runs parallel, otherwise the main pair (serial)
+Streams target_streams_of(const drl_apex* h) {
+  Streams st;
+  st.main = h->par ? h->tmain : h->compute;
+  st.side = h->par ? h->tside : h->side;
+  for (int i = 0; i < 8; ++i) st.ev[i] = h->par ? h->tfj[i] : h->fj[i];
+  st.par = h->par;
+  return st;
+}
+
 Streams streams_of(const drl_apex* h) {
   Streams st;
   st.main = h->compute;
@@ -603,14 +616,27 @@ int alloc_acts(drl_apex* h, ApexActs& a, int cap) {
 int enqueue_forward_td(drl_apex* h, const ApexSlot& sl, int n, bool train, float* td_host, int* launches) {
   pdl_break(h->compute);
   pdl_break(h->side);
-  const Streams st = streams_of(h);
+  const Streams st = streams_of(h), tst = target_streams_of(h);
+  // the target forward has no dependence on the main forward: fork it onto its own stream pair first, join before the
+  // TD kernel (inside a captured step these become parallel branches of the graph)
+  if (h->par) {
+    DRL_CUDA_CHECK(cudaEventRecord(h->ev_tfork, h->compute));
+    DRL_CUDA_CHECK(cudaStreamWaitEvent(h->tmain, h->ev_tfork, 0));
+    pdl_break(h->tmain);
+    pdl_break(h->tside);
+  }
+  DRL_TRY(apex_forward(tst, h->pl, h->target, h->twi, sl.frames + (size_t)n * Geo::FRAME, sl.pa2 + n, h->tact, n, h->mode,
+                       h->target_images_stale, false, true, launches));
+  h->target_images_stale = false;
+  if (h->par) DRL_CUDA_CHECK(cudaEventRecord(h->ev_tjoin, h->tmain));
   // rows [0, n) = s with previous_action, rows [n, 2n) = s' with action: one main-network forward covers both
   DRL_TRY(apex_forward(st, h->pl, h->params, h->wi, sl.frames, sl.pa2, h->act, 2 * n, h->mode, h->main_images_stale,
                        h->main_images_stale, false, launches));
   h->main_images_stale = false;
-  DRL_TRY(apex_forward(st, h->pl, h->target, h->twi, sl.frames + (size_t)n * Geo::FRAME, sl.pa2 + n, h->tact, n, h->mode,
-                       h->target_images_stale, false, true, launches));
-  h->target_images_stale = false;
+  if (h->par) {
+    DRL_CUDA_CHECK(cudaStreamWaitEvent(h->compute, h->ev_tjoin, 0));
+    pdl_break(h->compute);
+  }
   TdArgs a{};
   a.vstream = h->act.vstream; a.mstream = h->act.mstream;
   a.tvstream = h->tact.vstream; a.tmstream = h->tact.mstream;
@@ -737,6 +763,11 @@ int drl_apex_create(const drl_apex_config* cfg, drl_apex** out) {
     DRL_CUDA_CHECK(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
     DRL_CUDA_CHECK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
     for (int i = 0; i < 8; ++i) DRL_CUDA_CHECK(cudaEventCreateWithFlags(&h->fj[i], cudaEventDisableTiming));
+    DRL_CUDA_CHECK(cudaStreamCreateWithFlags(&h->tmain, cudaStreamNonBlocking));
+    DRL_CUDA_CHECK(cudaStreamCreateWithFlags(&h->tside, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; ++i) DRL_CUDA_CHECK(cudaEventCreateWithFlags(&h->tfj[i], cudaEventDisableTiming));
+    DRL_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_tfork, cudaEventDisableTiming));
+    DRL_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_tjoin, cudaEventDisableTiming));
     DRL_CUDA_CHECK(cudaEventCreate(&h->ev_start));
     DRL_CUDA_CHECK(cudaEventCreate(&h->ev_stop));
     DRL_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
@@ -853,6 +884,11 @@ int drl_apex_destroy(drl_apex* h) {
   if (h->ev_stop) cudaEventDestroy(h->ev_stop);
   if (h->ev_done) cudaEventDestroy(h->ev_done);
   for (int i = 0; i < 8; ++i) if (h->fj[i]) cudaEventDestroy(h->fj[i]);
+  for (int i = 0; i < 8; ++i) if (h->tfj[i]) cudaEventDestroy(h->tfj[i]);
+  if (h->ev_tfork) cudaEventDestroy(h->ev_tfork);
+  if (h->ev_tjoin) cudaEventDestroy(h->ev_tjoin);
+  if (h->tmain) cudaStreamDestroy(h->tmain);
+  if (h->tside) cudaStreamDestroy(h->tside);
   if (h->side) cudaStreamDestroy(h->side);
   if (h->compute) cudaStreamDestroy(h->compute);
   if (h->copy) cudaStreamDestroy(h->copy);

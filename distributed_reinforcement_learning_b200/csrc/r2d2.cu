@@ -626,6 +626,9 @@ struct drl_r2d2 {
   cudaStream_t compute = nullptr, copy = nullptr, side = nullptr;
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done = nullptr;
   cudaEvent_t fj[8] = {};
+  // the target scope's forward is independent of the main scope's: it runs on its own stream pair beside it
+  cudaStream_t tmain = nullptr, tside = nullptr;
+  cudaEvent_t tfj[8] = {}, ev_tfork = nullptr, ev_tjoin = nullptr;
   bool par = true;
   float *params = nullptr, *target = nullptr, *adam_m = nullptr, *adam_v = nullptr, *grads = nullptr;
   R2Acts act{}, tact{};
@@ -681,6 +684,16 @@ int download_flat(drl_r2d2* h, const float* dev_padded, float* host_packed) {
     memcpy(host_packed + h->pl.packed_off[i], h->h_flat + h->pl.padded_off[i], h->pl.count[i] * sizeof(float));
   return DRL_OK;
 }
+// stream pair of the target scope: its own pair when the step runs parallel, otherwise the main pair (serial)
+Streams target_streams_of(const drl_r2d2* h) {
+  Streams st;
+  st.main = h->par ? h->tmain : h->compute;
+  st.side = h->par ? h->tside : h->side;
+  for (int i = 0; i < 8; ++i) st.ev[i] = h->par ? h->tfj[i] : h->fj[i];
+  st.par = h->par;
+  return st;
+}
+
 Streams streams_of(const drl_r2d2* h) {
   Streams st;
   st.main = h->compute;
@@ -716,13 +729,26 @@ int alloc_acts(drl_r2d2* h, R2Acts& a) {
 int enqueue_forward_td(drl_r2d2* h, const R2In& in, int nb, bool train, float* td_host, int* launches) {
   pdl_break(h->compute);
   pdl_break(h->side);
-  const Streams st = streams_of(h);
+  const Streams st = streams_of(h), tst = target_streams_of(h);
+  // the two unrolls are independent (and each recurrence kernel only occupies nb SMs): the target scope runs on its
+  // own stream pair beside the main scope and joins before the TD kernel
+  if (h->par) {
+    DRL_CUDA_CHECK(cudaEventRecord(h->ev_tfork, h->compute));
+    DRL_CUDA_CHECK(cudaStreamWaitEvent(h->tmain, h->ev_tfork, 0));
+    pdl_break(h->tmain);
+    pdl_break(h->tside);
+  }
+  DRL_TRY(r2_forward(tst, h->pl, h->target, h->twi, in, h->tact, nullptr, nb, h->S, h->mode, h->target_images_stale, false,
+                     true, launches));
+  h->target_images_stale = false;
+  if (h->par) DRL_CUDA_CHECK(cudaEventRecord(h->ev_tjoin, h->tmain));
   DRL_TRY(r2_forward(st, h->pl, h->params, h->wi, in, h->act, nullptr, nb, h->S, h->mode, h->main_images_stale,
                      h->main_images_stale, false, launches));
   h->main_images_stale = false;
-  DRL_TRY(r2_forward(st, h->pl, h->target, h->twi, in, h->tact, nullptr, nb, h->S, h->mode, h->target_images_stale, false,
-                     true, launches));
-  h->target_images_stale = false;
+  if (h->par) {
+    DRL_CUDA_CHECK(cudaStreamWaitEvent(h->compute, h->ev_tjoin, 0));
+    pdl_break(h->compute);
+  }
   R2TdArgs a{};
   a.mq = h->act.q; a.tq = h->tact.q;
   a.action = in.action; a.reward = in.reward; a.done = in.done; a.weight = train ? in.weight : nullptr;
@@ -851,6 +877,11 @@ int drl_r2d2_create(const drl_r2d2_config* cfg, drl_r2d2** out) {
     DRL_CUDA_CHECK(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
     DRL_CUDA_CHECK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
     for (int i = 0; i < 8; ++i) DRL_CUDA_CHECK(cudaEventCreateWithFlags(&h->fj[i], cudaEventDisableTiming));
+    DRL_CUDA_CHECK(cudaStreamCreateWithFlags(&h->tmain, cudaStreamNonBlocking));
+    DRL_CUDA_CHECK(cudaStreamCreateWithFlags(&h->tside, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; ++i) DRL_CUDA_CHECK(cudaEventCreateWithFlags(&h->tfj[i], cudaEventDisableTiming));
+    DRL_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_tfork, cudaEventDisableTiming));
+    DRL_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_tjoin, cudaEventDisableTiming));
     DRL_CUDA_CHECK(cudaEventCreate(&h->ev_start));
     DRL_CUDA_CHECK(cudaEventCreate(&h->ev_stop));
     DRL_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
@@ -976,6 +1007,11 @@ int drl_r2d2_destroy(drl_r2d2* h) {
   if (h->ev_stop) cudaEventDestroy(h->ev_stop);
   if (h->ev_done) cudaEventDestroy(h->ev_done);
   for (int i = 0; i < 8; ++i) if (h->fj[i]) cudaEventDestroy(h->fj[i]);
+  for (int i = 0; i < 8; ++i) if (h->tfj[i]) cudaEventDestroy(h->tfj[i]);
+  if (h->ev_tfork) cudaEventDestroy(h->ev_tfork);
+  if (h->ev_tjoin) cudaEventDestroy(h->ev_tjoin);
+  if (h->tmain) cudaStreamDestroy(h->tmain);
+  if (h->tside) cudaStreamDestroy(h->tside);
   if (h->side) cudaStreamDestroy(h->side);
   if (h->compute) cudaStreamDestroy(h->compute);
   if (h->copy) cudaStreamDestroy(h->copy);
