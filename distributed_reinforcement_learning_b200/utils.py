@@ -3,8 +3,10 @@
   check_properties   utils.py:34-45  (config validation before the learner is built)
   copy_src_to_dst    utils.py:6-22   (learner -> actor variable copy; here a callable shim)
 
-The actor-side trajectory accumulators (utils.py:47-119) are out of scope.
+  UnrolledTrajectory utils.py:80-119  (the actor-side accumulator whose ``extract()`` feeds ``FIFOQueue.append_to_queue``,
+                                       train_impala.py:117,165-189: closes the actor -> ring -> learner loop)
 """
+import collections
 
 
 def check_properties(data):
@@ -28,3 +30,25 @@ def copy_src_to_dst(from_scope, to_scope):
         if dst is not None:
             dst.parameter_sync()
     return run
+
+
+class UnrolledTrajectory:
+    """utils.py:80-119: per-actor accumulator of one unroll; ``extract()`` returns the nine per-step lists that
+    ``FIFOQueue.append_to_queue`` takes (train_impala.py:178-189)."""
+
+    def __init__(self):
+        self.trajectory_data = collections.namedtuple(
+            'trajectory_data',
+            ['state', 'next_state', 'reward', 'done', 'action', 'behavior_policy', 'previous_action',
+             'initial_h', 'initial_c'])
+
+    def initialize(self):
+        self.unroll_data = self.trajectory_data(*[[] for _ in range(9)])
+
+    def append(self, state, next_state, reward, done, action, behavior_policy, previous_action, initial_h, initial_c):
+        for field, value in zip(self.unroll_data, (state, next_state, reward, done, action, behavior_policy,
+                                                   previous_action, initial_h, initial_c)):
+            field.append(value)
+
+    def extract(self):
+        return dict(self.unroll_data._asdict())
