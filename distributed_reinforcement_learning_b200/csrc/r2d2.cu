@@ -121,16 +121,20 @@ struct R2XA {
 static SplitPlan plan_r2_x(int M, int mode) {
   return mode >= 2 ? plan_split(kR2Cat, cdiv(M, 128), 32, 1) : plan_split(kR2Cat, cdiv(M, CfgMid::BM) * (kR2G / CfgMid::BN), 16, 1);
 }
-static SplitPlan plan_r2_conv1_wgrad(int M, int mode) {
-  return mode >= 2 ? plan_split(M * 400, 1, 32, 2) : plan_split(M * 400, 1, 16, 2);
-}
+// conv1 weight gradient with single-channel frames is a [64 x 32] output with K = M*400: half of a 128-row MMA tile
+// would be padding and the producers, not the tensor pipe, set the pace (measured 0.20 ms at M = 1280 on the tcgen05
+// core).  A 64 x 32 FFMA tile with the reduction split over ~4 CTAs per SM fits the shape in both math modes.
+using CfgWgC1 = TileCfg<64, 32, 16, 4, 4>;
+static SplitPlan plan_r2_conv1_wgrad(int M, int) { return plan_split(M * 400, 1, 16, 4); }
 
 // ------------------------------------------------------------------------------------------
 // LSTM recurrence, forward (model/r2d2_lstm.py:12-21 inside the unroll :67-84; TF 1.14 LSTMCell):
 //   z_t = sum_s zpart[s][m] + b + h_in W_h ; i,j,f,o = split(z_t)
 //   c_t = sigmoid(f + 1) c_in + sigmoid(i) tanh(j) ; h_t = sigmoid(o) tanh(c_t)         (h_t feeds the q head)
 //   (h_in, c_in) of step t+1 = (h_t, c_t) * (1 - done_t)
-// One CTA per sequence, 4L = 256 threads (thread j owns gate column j), W_h [L][4L] in shared memory.
+// One CTA per sequence, 4L = 256 threads; thread j owns gate column j and keeps W_h[:, j] (L = 64 floats) in REGISTERS for
+// all S steps: with W_h in shared memory every step re-read its 64 KB (512 clk of LDS bandwidth per SM, measured
+// 1.36 us per step); from registers a step costs 16 broadcast LDS.128 of h plus 64 FMAs per thread.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kR2G) r2d2_lstm_fwd_kernel(
     const float* __restrict__ zpart, int nsplit, size_t slab, const float* __restrict__ bias,
@@ -138,43 +142,60 @@ __global__ void __launch_bounds__(kR2G) r2d2_lstm_fwd_kernel(
     const uint8_t* __restrict__ done, float* __restrict__ gates, float* __restrict__ tc, float* __restrict__ hout,
     float* __restrict__ hin, float* __restrict__ cin, float* __restrict__ c_last, int B, int S) {
   pdl_prologue();
-  extern __shared__ __align__(16) float sm[];
-  float* sW = sm;                       // [L][4L]
-  float* sh = sm + kR2L * kR2G;         // [L]
-  float* sz = sh + kR2L;                // [4L]
+  __shared__ __align__(16) float sh[kR2L];
+  __shared__ float sz[kR2G];
   const int b = blockIdx.x, j = threadIdx.x;
-  for (int i = j; i < kR2L * kR2G; i += kR2G) sW[i] = Wh[i];
+  float w[kR2L];
+#pragma unroll
+  for (int k = 0; k < kR2L; ++k) w[k] = Wh[k * kR2G + j];      // coalesced across the CTA, once
   float c_reg = 0.f;
   if (j < kR2L) { sh[j] = h0[(size_t)b * kR2L + j]; c_reg = c0[(size_t)b * kR2L + j]; }
   const float bj = bias[j];
+  // the step input z_x[t] and done[t] do not depend on the recurrence: the loads of step t+1 are issued at the top of
+  // step t so that their latency (L2 / HBM) is off the serial chain
+  auto load_z = [&](int t) {
+    const size_t m = (size_t)t * B + b;
+    float z = 0.f;
+    for (int s = 0; s < nsplit; ++s) z += zpart[(size_t)s * slab + m * kR2G + j];
+    return z;
+  };
+  float z_next = load_z(0);
+  float keep_next = (done && done[(size_t)b * S]) ? 0.f : 1.f;
   __syncthreads();
   for (int t = 0; t < S; ++t) {
     const size_t m = (size_t)t * B + b;
-    float z = bj;
-    for (int s = 0; s < nsplit; ++s) z += zpart[(size_t)s * slab + m * kR2G + j];
-    float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll 8
-    for (int k = 0; k < kR2L; k += 2) {
-      acc0 = fmaf(sh[k], sW[k * kR2G + j], acc0);
-      acc1 = fmaf(sh[k + 1], sW[(k + 1) * kR2G + j], acc1);
+    const float z = bj + z_next;
+    const float keep = keep_next;
+    if (t + 1 < S) {
+      z_next = load_z(t + 1);
+      keep_next = (done && done[(size_t)b * S + t + 1]) ? 0.f : 1.f;
     }
-    sz[j] = z + (acc0 + acc1);
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;      // four independent chains: 16 dependent FMAs each
+#pragma unroll
+    for (int k = 0; k < kR2L; k += 4) {
+      const float4 h4 = *reinterpret_cast<const float4*>(sh + k);     // broadcast
+      acc0 = fmaf(h4.x, w[k], acc0);
+      acc1 = fmaf(h4.y, w[k + 1], acc1);
+      acc2 = fmaf(h4.z, w[k + 2], acc2);
+      acc3 = fmaf(h4.w, w[k + 3], acc3);
+    }
+    // every thread applies the nonlinearity of its own gate column (warp-uniform branch: L = 2 warps per gate), so
+    // the serial tail below is left with one tanh instead of five transcendentals
+    const float pre = z + ((acc0 + acc1) + (acc2 + acc3));
+    const int gate = j / kR2L;
+    const float actv = (gate == 1) ? tanhf(pre) : sigmoidf_acc(gate == 2 ? pre + 1.0f : pre);
+    sz[j] = actv;
+    gates[m * kR2G + j] = actv;
     if (j < kR2L) { hin[m * kR2L + j] = sh[j]; cin[m * kR2L + j] = c_reg; }
     __syncthreads();
     if (j < kR2L) {
-      const float si = sigmoidf_acc(sz[j]);
-      const float tj = tanhf(sz[kR2L + j]);
-      const float sf = sigmoidf_acc(sz[2 * kR2L + j] + 1.0f);
-      const float so = sigmoidf_acc(sz[3 * kR2L + j]);
+      const float si = sz[j], tj = sz[kR2L + j], sf = sz[2 * kR2L + j], so = sz[3 * kR2L + j];
       const float c = sf * c_reg + si * tj;
       const float tcv = tanhf(c);
       const float h = so * tcv;
-      float* g = gates + m * kR2G;
-      g[j] = si; g[kR2L + j] = tj; g[2 * kR2L + j] = sf; g[3 * kR2L + j] = so;
       tc[m * kR2L + j] = tcv;
       hout[m * kR2L + j] = h;
       if (c_last) c_last[m * kR2L + j] = c;
-      const float keep = done ? (done[(size_t)b * S + t] ? 0.f : 1.f) : 1.f;
       c_reg = c * keep;
       sh[j] = h * keep;
     }
@@ -185,56 +206,73 @@ __global__ void __launch_bounds__(kR2G) r2d2_lstm_fwd_kernel(
 // BPTT through the same recurrence (rows of all S steps receive gradient):
 //   dh_t = dhout[m] + (1 - done_t) dh_in[t+1] ; dc_t = (1 - done_t) dc_in[t+1] + dh_t so (1 - tc^2)
 //   do = dh_t tc so(1-so) ; di = dc_t tj si(1-si) ; dj = dc_t si (1 - tj^2) ; df = dc_t c_in sf(1-sf)
-//   dc_in[t] = dc_t sf ; dh_in[t] = dz_t W_h^T
+//   dc_in[t] = dc_t sf ; dh_in[t] = dz_t W_h^T        (the weights again live in registers, 64 per thread)
 __global__ void __launch_bounds__(kR2G) r2d2_lstm_bwd_kernel(
     const float* __restrict__ dhout, const float* __restrict__ gates, const float* __restrict__ tc,
     const float* __restrict__ cin, const float* __restrict__ Wh, const uint8_t* __restrict__ done,
     float* __restrict__ dz, int B, int S) {
   pdl_prologue();
-  extern __shared__ __align__(16) float sm[];
-  float* sWT = sm;                      // [4L][L]  (W_h transposed)
-  float* sdz = sm + kR2L * kR2G;        // [4L]
-  float* sdh = sdz + kR2G;              // [L]
-  float* spart = sdh + kR2L;            // [4][L]
+  __shared__ __align__(16) float sdz[kR2G];
+  __shared__ float sdh[kR2L];
+  __shared__ float spart[4 * kR2L];
   const int b = blockIdx.x, tid = threadIdx.x;
-  for (int i = tid; i < kR2L * kR2G; i += kR2G) {
-    const int k = i / kR2G, jj = i - k * kR2G;      // Wh[k][jj]
-    sWT[jj * kR2L + k] = Wh[i];
-  }
+  const int kk = tid & (kR2L - 1), q = tid / kR2L;
+  // thread (kk, q) accumulates dh_in[kk] over gate columns [q L, (q+1) L): its 64 weights W_h[kk][q L + i] stay in registers
+  float w[kR2L];
+#pragma unroll
+  for (int i = 0; i < kR2L; ++i) w[i] = Wh[(size_t)kk * kR2G + q * kR2L + i];
   float dc_carry = 0.f;
   if (tid < kR2L) sdh[tid] = 0.f;
   __syncthreads();
-  const int kk = tid & (kR2L - 1), q = tid / kR2L;
+  // operands of step t-1 are fetched while step t computes (they do not depend on the recurrence)
+  struct Ops { float dho, si, tj, sf, so, tcv, cprev, keep; };
+  auto fetch = [&](int t) {
+    Ops o{};
+    if (tid < kR2L) {
+      const size_t m = (size_t)t * B + b;
+      const float* g = gates + m * kR2G;
+      o.dho = dhout[m * kR2L + tid];
+      o.si = g[tid]; o.tj = g[kR2L + tid]; o.sf = g[2 * kR2L + tid]; o.so = g[3 * kR2L + tid];
+      o.tcv = tc[m * kR2L + tid];
+      o.cprev = cin[m * kR2L + tid];
+      o.keep = done[(size_t)b * S + t] ? 0.f : 1.f;
+    }
+    return o;
+  };
+  Ops nxt = fetch(S - 1);
   for (int t = S - 1; t >= 0; --t) {
     const size_t m = (size_t)t * B + b;
+    const Ops cur = nxt;
+    if (t > 0) nxt = fetch(t - 1);
     if (tid < kR2L) {
-      const float keep = done[(size_t)b * S + t] ? 0.f : 1.f;
-      const float dh = dhout[m * kR2L + tid] + keep * sdh[tid];
-      const float* g = gates + m * kR2G;
-      const float si = g[tid], tj = g[kR2L + tid], sf = g[2 * kR2L + tid], so = g[3 * kR2L + tid];
-      const float tcv = tc[m * kR2L + tid];
-      const float cprev = cin[m * kR2L + tid];
+      const float keep = cur.keep;
+      const float dh = cur.dho + keep * sdh[tid];
+      const float si = cur.si, tj = cur.tj, sf = cur.sf, so = cur.so;
+      const float tcv = cur.tcv;
+      const float cprev = cur.cprev;
       const float d_o = dh * tcv * so * (1.f - so);
       const float dc = keep * dc_carry + dh * so * (1.f - tcv * tcv);
       const float di = dc * tj * si * (1.f - si);
       const float dj = dc * si * (1.f - tj * tj);
       const float df = dc * cprev * sf * (1.f - sf);
       sdz[tid] = di; sdz[kR2L + tid] = dj; sdz[2 * kR2L + tid] = df; sdz[3 * kR2L + tid] = d_o;
-      float* d = dz + m * kR2G;
-      d[tid] = di; d[kR2L + tid] = dj; d[2 * kR2L + tid] = df; d[3 * kR2L + tid] = d_o;
       dc_carry = dc * sf;
     }
     __syncthreads();
-    float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll 8
-    for (int jj = q * kR2L; jj < (q + 1) * kR2L; jj += 2) {
-      acc0 = fmaf(sdz[jj], sWT[jj * kR2L + kk], acc0);
-      acc1 = fmaf(sdz[jj + 1], sWT[(jj + 1) * kR2L + kk], acc1);
+    dz[m * kR2G + tid] = sdz[tid];                    // coalesced store of the step's 4L gate gradients
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kR2L; i += 4) {
+      const float4 d4 = *reinterpret_cast<const float4*>(sdz + q * kR2L + i);   // broadcast within the warp
+      acc0 = fmaf(d4.x, w[i], acc0);
+      acc1 = fmaf(d4.y, w[i + 1], acc1);
+      acc2 = fmaf(d4.z, w[i + 2], acc2);
+      acc3 = fmaf(d4.w, w[i + 3], acc3);
     }
-    spart[q * kR2L + kk] = acc0 + acc1;
+    spart[q * kR2L + kk] = (acc0 + acc1) + (acc2 + acc3);
     __syncthreads();
+    // sdh[tid] is only read by the thread that writes it; spart / sdz are protected by the two barriers above
     if (tid < kR2L) sdh[tid] = (spart[tid] + spart[kR2L + tid]) + (spart[2 * kR2L + tid] + spart[3 * kR2L + tid]);
-    __syncthreads();
   }
 }
 
@@ -310,8 +348,13 @@ __global__ void __launch_bounds__(256) r2d2_td_kernel(R2TdArgs a) {
   __shared__ float red[8];
   const int Nt = a.S - a.burn_in - 1;
   const int M = a.B * a.S;
-  if (a.dq) {
-    for (int i = threadIdx.x; i < M * 32; i += blockDim.x) { a.dq[i] = 0.f; a.dmean[i] = 0.f; }
+  if (a.dq) {      // rows outside the loss window carry no gradient; columns >= A / >= 1 are never written (stay zero)
+    const int W = a.A + 1;
+    for (int i = threadIdx.x; i < M * W; i += blockDim.x) {
+      const int m = i / W, k = i - m * W;
+      if (k < a.A) a.dq[(size_t)m * 32 + k] = 0.f;
+      else a.dmean[(size_t)m * 32] = 0.f;
+    }
     __syncthreads();
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -380,8 +423,7 @@ static int join_from_side(const Streams& st, int i) {
   return DRL_OK;
 }
 
-constexpr size_t kR2FwdSmem = (size_t)(kR2L * kR2G + kR2L + kR2G) * sizeof(float);
-constexpr size_t kR2BwdSmem = (size_t)(kR2L * kR2G + kR2G + kR2L + 4 * kR2L) * sizeof(float);
+constexpr size_t kR2FwdSmem = 0, kR2BwdSmem = 0;     // the recurrence kernels only use small static shared arrays
 
 // Forward of one scope over B sequences of S steps (rows m = t*B + b).  c_last (optional): un-masked c_t (act path).
 static int r2_forward(const Streams& st, const R2Layout& pl, const float* P, const WeightImages& wi, const R2In& in,
@@ -591,7 +633,7 @@ static int r2_backward(const Streams& st, const R2Layout& pl, const float* P, co
     Conv1WA1 al{in.frames, map};
     PlainB bl{bw.da1, 32, 0};
     EpRaw<true> ep{bw.wg_part2, 32, slab, 1.0f / 255.0f, 64, 32};
-    GEMM("conv1_wgrad", CfgWg1, U32, al, bl, ep, 64, 32, M * 400, sp.splits, sp.kchunk, sp.kchunk);
+    GEMM_FFMA("conv1_wgrad", CfgWgC1, al, bl, ep, 64, 32, M * 400, sp.splits, sp.kchunk, sp.kchunk);
     KERNEL("conv1_wgrad_reduce", splitk_reduce(s, bw.wg_part2, slab, sp.splits, G + pl.conv1_w, slab), 1);
   } else {
     const SplitPlan sp = plan_conv1_wgrad(M, mode);
@@ -885,8 +927,6 @@ int drl_r2d2_create(const drl_r2d2_config* cfg, drl_r2d2** out) {
     DRL_CUDA_CHECK(cudaEventCreate(&h->ev_start));
     DRL_CUDA_CHECK(cudaEventCreate(&h->ev_stop));
     DRL_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
-    DRL_CUDA_CHECK(cudaFuncSetAttribute(r2d2_lstm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kR2FwdSmem));
-    DRL_CUDA_CHECK(cudaFuncSetAttribute(r2d2_lstm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kR2BwdSmem));
     const size_t B = h->B, S = h->S, M = B * S, A = h->A, NP = h->pl.padded_total;
     DRL_TRY(dev_alloc(h, &h->params, NP));
     DRL_TRY(dev_alloc(h, &h->target, NP));
