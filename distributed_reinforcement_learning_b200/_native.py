@@ -53,6 +53,19 @@ class ApexOut(C.Structure):
     _fields_ = [("loss", C.c_float), ("learning_rate", C.c_float), ("grad_norm", C.c_float), ("step", C.c_int64)]
 
 
+class A3cConfig(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("height", C.c_int32), ("width", C.c_int32), ("channels", C.c_int32),
+                ("num_action", C.c_int32), ("discount_factor", C.c_float), ("start_learning_rate", C.c_float),
+                ("end_learning_rate", C.c_float), ("learning_frame", C.c_double), ("baseline_loss_coef", C.c_float),
+                ("entropy_coef", C.c_float), ("gradient_clip_norm", C.c_float), ("reward_clipping", C.c_int32),
+                ("device", C.c_int32), ("num_slots", C.c_int32), ("use_cuda_graph", C.c_int32), ("math_mode", C.c_int32)]
+
+
+class A3cOut(C.Structure):
+    _fields_ = [("pi_loss", C.c_float), ("baseline_loss", C.c_float), ("entropy", C.c_float),
+                ("learning_rate", C.c_float), ("grad_norm", C.c_float), ("step", C.c_int64)]
+
+
 class R2d2Config(C.Structure):
     _fields_ = [("batch", C.c_int32), ("seq_len", C.c_int32), ("burn_in", C.c_int32), ("height", C.c_int32),
                 ("width", C.c_int32), ("channels", C.c_int32), ("num_action", C.c_int32), ("lstm_size", C.c_int32),
@@ -143,6 +156,24 @@ def _load():
         "drl_apex_last_step_ms": (C.c_int, [vp, C.POINTER(f32)]),
         "drl_apex_launches_per_step": (C.c_int, [vp, C.POINTER(i32)]),
         "drl_apex_stream": (C.c_int, [vp, C.POINTER(vp)]),
+        "drl_a3c_create": (C.c_int, [C.POINTER(A3cConfig), C.POINTER(vp)]),
+        "drl_a3c_destroy": (C.c_int, [vp]),
+        "drl_a3c_param_count": (C.c_int, [vp, C.POINTER(i64)]),
+        "drl_a3c_set_params": (C.c_int, [vp, vp, i64]),
+        "drl_a3c_get_params": (C.c_int, [vp, vp, i64]),
+        "drl_a3c_set_opt_state": (C.c_int, [vp, vp, vp, i64, i64, f32, f32]),
+        "drl_a3c_get_opt_state": (C.c_int, [vp, vp, vp, i64, C.POINTER(i64), C.POINTER(f32), C.POINTER(f32)]),
+        "drl_a3c_get_grads": (C.c_int, [vp, vp, i64]),
+        "drl_a3c_stage": (C.c_int, [vp, i32] + [vp] * 6),
+        "drl_a3c_step": (C.c_int, [vp, i32, C.POINTER(A3cOut)]),
+        "drl_a3c_step_async": (C.c_int, [vp, i32]),
+        "drl_a3c_wait": (C.c_int, [vp, C.POINTER(A3cOut)]),
+        "drl_a3c_act": (C.c_int, [vp, i32, vp, vp, vp, vp]),
+        "drl_a3c_taps": (C.c_int, [vp] * 5),
+        "drl_a3c_read_buffer": (C.c_int, [vp, C.c_char_p, vp, i64]),
+        "drl_a3c_profile_step": (C.c_int, [vp, i32, C.c_char_p, i64, vp, i32, C.POINTER(i32)]),
+        "drl_a3c_stream": (C.c_int, [vp, C.POINTER(vp)]),
+        "drl_a3c_launches_per_step": (C.c_int, [vp, C.POINTER(i32)]),
         "drl_r2d2_create": (C.c_int, [C.POINTER(R2d2Config), C.POINTER(vp)]),
         "drl_r2d2_destroy": (C.c_int, [vp]),
         "drl_r2d2_param_count": (C.c_int, [vp, C.POINTER(i64)]),

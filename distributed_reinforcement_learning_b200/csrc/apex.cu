@@ -169,6 +169,71 @@ __global__ void __launch_bounds__(256) apex_td_kernel(TdArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
+// A3C / A2C losses and head gradients (optimizer/a2c.py:3-26, agent/a3c.py:36-73) on the same network body: the actor
+// stream ends in a softmax (model/actor_critic.py:33-34), the critic stream is the scalar value.  Rows [0, n) hold
+// network(s, prev_a), rows [n, 2n) network(s', a); next_value is stop_gradient in both losses.
+//   adv      = clip(r) + gamma (1 - done) V(s') - V(s)                      (stop_gradient in the policy loss)
+//   pi_loss  = -mean(adv * pi(a))        (the probability itself, not its log: optimizer/a2c.py:24)
+//   baseline = mean(adv^2) ; entropy = -mean(sum_a -pi log pi)              (no epsilon, like the reference)
+//   total    = pi_loss + baseline_coef baseline + entropy_coef entropy
+// ------------------------------------------------------------------------------------------
+struct A3cArgs {
+  const float* policy; const float* value;      // [2n, A], [2n]
+  const int32_t* action; const float* reward; const uint8_t* done;
+  float discount, baseline_coef, entropy_coef; int clip; int n, A;
+  float* adv;                                   // [n] tap
+  float* dlogits; float* dv;                    // [n, 32]
+  float* loss;                                  // [3] pi, baseline, entropy
+};
+__global__ void __launch_bounds__(256) a3c_loss_kernel(A3cArgs a) {
+  pdl_prologue();
+  __shared__ float red[3][8];
+  float s_pi = 0.f, s_bl = 0.f, s_en = 0.f;
+  const float inv_n = 1.0f / (float)a.n;
+  for (int b = threadIdx.x; b < a.n; b += blockDim.x) {
+    float r = a.reward[b];
+    if (a.clip == DRL_REWARD_ABS_ONE) {
+      r = fminf(fmaxf(r, -1.0f), 1.0f);
+    } else {                                          // soft_asymmetric (agent/a3c.py:41-43)
+      const float sq = tanhf(r / 5.0f);
+      r = (r < 0.f ? 0.3f * sq : sq) * 5.0f;
+    }
+    const float disc = a.done[b] ? 0.0f : a.discount;
+    const float adv = r + disc * a.value[a.n + b] - a.value[b];
+    a.adv[b] = adv;
+    const int act = a.action[b];
+    const float* p = a.policy + (size_t)b * a.A;
+    float ent = 0.f, sdot = 0.f;
+    for (int k = 0; k < a.A; ++k) {
+      const float pk = p[k], lp = logf(pk);
+      ent += pk * lp;
+      const float dpk = ((k == act ? -adv : 0.f) + a.entropy_coef * (lp + 1.0f)) * inv_n;     // d total / d pi_k
+      sdot += pk * dpk;
+    }
+    for (int k = 0; k < a.A; ++k) {                   // through the softmax: dlogit_k = pi_k (dpi_k - sum_j pi_j dpi_j)
+      const float pk = p[k];
+      const float dpk = ((k == act ? -adv : 0.f) + a.entropy_coef * (logf(pk) + 1.0f)) * inv_n;
+      a.dlogits[(size_t)b * 32 + k] = pk * (dpk - sdot);
+    }
+    a.dv[(size_t)b * 32] = a.baseline_coef * (-2.0f * adv) * inv_n;
+    s_pi += adv * p[act];
+    s_bl += adv * adv;
+    s_en += ent;
+  }
+  s_pi = warp_sum(s_pi); s_bl = warp_sum(s_bl); s_en = warp_sum(s_en);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s_pi; red[1][threadIdx.x >> 5] = s_bl; red[2][threadIdx.x >> 5] = s_en; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { t0 += red[0][i]; t1 += red[1][i]; t2 += red[2][i]; }
+    a.loss[0] = -t0 * inv_n;
+    a.loss[1] = t1 * inv_n;
+    a.loss[2] = t2 * inv_n;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Tail of the train op (agent/apex.py:70-75) with TF 1.14 semantics:
 //   lr    = polynomial_decay(start, global_step, decay_steps, end)      (float32, pre-increment step)
 //   g    <- g * clip * min(1/||g||, 1/clip)                              (clip_by_global_norm over the main variables;
@@ -230,7 +295,8 @@ __global__ void __launch_bounds__(256) adam_apply_kernel(AdamState o) {
     const float norm = sqrtf(s);
     s_scale = (o.clip_norm > 0.f) ? o.clip_norm * fminf(1.0f / norm, 1.0f / o.clip_norm) : 1.0f;
     if (blockIdx.x == 0) {
-      o.out[0] = *o.loss; o.out[1] = *o.lr_cur; o.out[2] = norm;
+      o.out[0] = o.loss[0]; o.out[1] = *o.lr_cur; o.out[2] = norm;
+      o.out[3] = o.loss[1]; o.out[4] = o.loss[2];          // A3C: baseline loss, entropy (zero for the DQN learners)
       const long long st = *o.step;
       o.out[6] = __int_as_float((int)(st & 0xffffffffll));
       o.out[7] = __int_as_float((int)(st >> 32));
@@ -520,6 +586,11 @@ struct drl_apex {
   float *main_q = nullptr, *next_main_q = nullptr, *target_q = nullptr, *target_value = nullptr, *sav = nullptr,
         *td_dev = nullptr, *loss = nullptr;
   int last_n = 0;              // rows of the most recent step / td_error call (taps, read_buffer)
+  // A3C runs on the same body (drl_a3c_*): no target scope, the loss kernel above, three loss scalars
+  int algo = 0;                // 0 = Ape-X DQN, 1 = A3C
+  float a3c_baseline_coef = 0.f, a3c_entropy_coef = 0.f;
+  int a3c_clip = 0;
+  float* adv = nullptr;        // [B] advantage tap
   AdamState opt{};
   long long* d_step = nullptr;
   float *d_lr = nullptr, *d_alpha = nullptr, *d_b1p = nullptr, *d_b2p = nullptr;
@@ -617,6 +688,21 @@ int enqueue_forward_td(drl_apex* h, const ApexSlot& sl, int n, bool train, float
   pdl_break(h->compute);
   pdl_break(h->side);
   const Streams st = streams_of(h), tst = target_streams_of(h);
+  if (h->algo == 1) {      // A3C: one scope; rows [0, n) = network(s, prev_a), rows [n, 2n) = network(s', a)
+    DRL_TRY(apex_forward(st, h->pl, h->params, h->wi, sl.frames, sl.pa2, h->act, 2 * n, h->mode, h->main_images_stale,
+                         h->main_images_stale, false, launches));
+    h->main_images_stale = false;
+    A3cArgs a{};
+    a.policy = h->act.scratch_sm; a.value = h->act.mstream;
+    a.action = sl.pa2 + n; a.reward = sl.reward; a.done = sl.done;
+    a.discount = h->cfg.discount_factor; a.baseline_coef = h->a3c_baseline_coef; a.entropy_coef = h->a3c_entropy_coef;
+    a.clip = h->a3c_clip; a.n = n; a.A = h->A;
+    a.adv = h->adv; a.dlogits = h->bwd.dq; a.dv = h->bwd.dmean; a.loss = h->loss;
+    prof_mark(h->compute, "a2c_losses");
+    DRL_CUDA_CHECK((launch_k(a3c_loss_kernel, 1, 256, 0, h->compute, a)));
+    if (launches) *launches += 1;
+    return DRL_OK;
+  }
   // the target forward has no dependence on the main forward: fork it onto its own stream pair first, join before the
   // TD kernel (inside a captured step these become parallel branches of the graph)
   if (h->par) {
@@ -807,6 +893,7 @@ int drl_apex_create(const drl_apex_config* cfg, drl_apex** out) {
     DRL_TRY(dev_alloc(h, &h->sav, B));
     DRL_TRY(dev_alloc(h, &h->td_dev, B));
     DRL_TRY(dev_alloc(h, &h->loss, 4));
+    DRL_TRY(dev_alloc(h, &h->adv, B));
     DRL_TRY(dev_alloc(h, &h->d_step, 1));
     DRL_TRY(dev_alloc(h, &h->d_lr, 1));
     DRL_TRY(dev_alloc(h, &h->d_alpha, 1));
@@ -1155,5 +1242,101 @@ int drl_apex_launches_per_step(const drl_apex* h, int32_t* n) {
   *n = h->launches;     // valid after the first step
   return DRL_OK;
 }
+
+// ---- A3C learner: the same handle type with algo = 1 (include/drl_b200.h) ---------------------------------------
+int drl_a3c_create(const drl_a3c_config* cfg, drl_a3c** out) {
+  if (!cfg || !out) { set_error("null argument"); return DRL_ERR_INVALID; }
+  *out = nullptr;
+  if (cfg->reward_clipping != DRL_REWARD_ABS_ONE && cfg->reward_clipping != DRL_REWARD_SOFT_ASYMMETRIC) {
+    set_error("reward_clipping must be DRL_REWARD_ABS_ONE or DRL_REWARD_SOFT_ASYMMETRIC");
+    return DRL_ERR_INVALID;
+  }
+  drl_apex_config c{};
+  c.batch = cfg->batch; c.height = cfg->height; c.width = cfg->width; c.channels = cfg->channels;
+  c.num_action = cfg->num_action; c.discount_factor = cfg->discount_factor;
+  c.start_learning_rate = cfg->start_learning_rate; c.end_learning_rate = cfg->end_learning_rate;
+  c.learning_frame = cfg->learning_frame; c.gradient_clip_norm = cfg->gradient_clip_norm;
+  c.reward_clipping = cfg->reward_clipping; c.device = cfg->device; c.num_slots = cfg->num_slots;
+  c.use_cuda_graph = cfg->use_cuda_graph; c.math_mode = cfg->math_mode;
+  drl_apex* h = nullptr;
+  DRL_TRY(drl_apex_create(&c, &h));
+  h->algo = 1;
+  h->a3c_baseline_coef = cfg->baseline_loss_coef;
+  h->a3c_entropy_coef = cfg->entropy_coef;
+  h->a3c_clip = cfg->reward_clipping;
+  *out = h;
+  return DRL_OK;
+}
+int drl_a3c_destroy(drl_a3c* h) { return drl_apex_destroy(h); }
+int drl_a3c_param_count(const drl_a3c* h, int64_t* n) { return drl_apex_param_count(h, n); }
+int drl_a3c_set_params(drl_a3c* h, const float* host_flat, int64_t n) { return drl_apex_set_params(h, DRL_APEX_MAIN, host_flat, n); }
+int drl_a3c_get_params(drl_a3c* h, float* host_flat, int64_t n) { return drl_apex_get_params(h, DRL_APEX_MAIN, host_flat, n); }
+int drl_a3c_set_opt_state(drl_a3c* h, const float* m, const float* v, int64_t n, int64_t step, float b1p, float b2p) {
+  return drl_apex_set_opt_state(h, m, v, n, step, b1p, b2p);
+}
+int drl_a3c_get_opt_state(drl_a3c* h, float* m, float* v, int64_t n, int64_t* step, float* b1p, float* b2p) {
+  return drl_apex_get_opt_state(h, m, v, n, step, b1p, b2p);
+}
+int drl_a3c_get_grads(drl_a3c* h, float* host_flat, int64_t n) { return drl_apex_get_grads(h, host_flat, n); }
+int drl_a3c_stage(drl_a3c* h, int32_t slot, const uint8_t* state, const uint8_t* next_state, const int32_t* previous_action,
+                  const int32_t* action, const float* reward, const uint8_t* done) {
+  return drl_apex_stage(h, slot, state, next_state, previous_action, action, reward, done, nullptr);
+}
+int drl_a3c_step_async(drl_a3c* h, int32_t slot) {
+  DRL_TRY(check_handle(h));
+  if (h->algo != 1) { set_error("not an A3C handle"); return DRL_ERR_INVALID; }
+  return drl_apex_step_async(h, slot);
+}
+int drl_a3c_wait(drl_a3c* h, drl_a3c_out* out) {
+  DRL_TRY(check_handle(h));
+  drl_apex_out o{};
+  DRL_TRY(drl_apex_wait(h, &o, nullptr));
+  if (out) {
+    const float* r = h->h_out + 8 * h->last_slot;
+    out->pi_loss = r[0]; out->baseline_loss = r[3]; out->entropy = r[4];
+    out->learning_rate = o.learning_rate; out->grad_norm = o.grad_norm; out->step = o.step;
+  }
+  return DRL_OK;
+}
+int drl_a3c_step(drl_a3c* h, int32_t slot, drl_a3c_out* out) {
+  DRL_TRY(drl_a3c_step_async(h, slot));
+  return drl_a3c_wait(h, out);
+}
+int drl_a3c_act(drl_a3c* h, int32_t n, const uint8_t* state, const int32_t* previous_action, float* policy, float* value) {
+  DRL_TRY(check_handle(h));
+  if (n < 1 || n > 2 * h->B) { set_error("act: n must be in [1, %d]", 2 * h->B); return DRL_ERR_INVALID; }
+  if (!state || !previous_action) { set_error("act: null pointer"); return DRL_ERR_INVALID; }
+  DRL_TRY(set_device(h));
+  ApexSlot& s = h->slots[h->cfg.num_slots];
+  DRL_CUDA_CHECK(cudaStreamSynchronize(h->compute));
+  DRL_TRY(stage_into(h, s, h->compute, n, n, state, nullptr, previous_action, nullptr, nullptr, nullptr, nullptr));
+  pdl_break(h->compute);
+  DRL_TRY(apex_forward(streams_of(h), h->pl, h->params, h->wi, s.frames, s.pa2, h->act, n, h->mode, h->main_images_stale,
+                       h->main_images_stale, false, nullptr));
+  h->main_images_stale = false;
+  if (policy) DRL_CUDA_CHECK(cudaMemcpyAsync(policy, h->act.scratch_sm, (size_t)n * h->A * 4, cudaMemcpyDeviceToHost, h->compute));
+  if (value) DRL_CUDA_CHECK(cudaMemcpyAsync(value, h->act.mstream, (size_t)n * 4, cudaMemcpyDeviceToHost, h->compute));
+  DRL_CUDA_CHECK(cudaStreamSynchronize(h->compute));
+  h->last_n = 0;
+  return DRL_OK;
+}
+int drl_a3c_taps(drl_a3c* h, float* policy, float* value, float* next_value, float* advantage) {
+  DRL_TRY(check_handle(h));
+  DRL_TRY(set_device(h));
+  if (h->last_n < 1) { set_error("taps: no step has run"); return DRL_ERR_STATE; }
+  DRL_CUDA_CHECK(cudaStreamSynchronize(h->compute));
+  const size_t n = h->last_n, A = h->A;
+  if (policy) DRL_CUDA_CHECK(cudaMemcpy(policy, h->act.scratch_sm, n * A * 4, cudaMemcpyDeviceToHost));
+  if (value) DRL_CUDA_CHECK(cudaMemcpy(value, h->act.mstream, n * 4, cudaMemcpyDeviceToHost));
+  if (next_value) DRL_CUDA_CHECK(cudaMemcpy(next_value, h->act.mstream + n, n * 4, cudaMemcpyDeviceToHost));
+  if (advantage) DRL_CUDA_CHECK(cudaMemcpy(advantage, h->adv, n * 4, cudaMemcpyDeviceToHost));
+  return DRL_OK;
+}
+int drl_a3c_read_buffer(drl_a3c* h, const char* name, float* host_dst, int64_t n) { return drl_apex_read_buffer(h, name, host_dst, n); }
+int drl_a3c_profile_step(drl_a3c* h, int32_t slot, char* names, int64_t names_len, float* ms, int32_t max_kernels, int32_t* count) {
+  return drl_apex_profile_step(h, slot, names, names_len, ms, max_kernels, count);
+}
+int drl_a3c_stream(drl_a3c* h, void** stream) { return drl_apex_stream(h, stream); }
+int drl_a3c_launches_per_step(const drl_a3c* h, int32_t* n) { return drl_apex_launches_per_step(h, n); }
 
 }  // extern "C"

@@ -449,6 +449,73 @@ int drl_r2d2_last_step_ms(drl_r2d2* h, float* ms);
 int drl_r2d2_stream(drl_r2d2* h, void** stream);
 int drl_r2d2_launches_per_step(const drl_r2d2* h, int32_t* n);
 
+/* ------------------------------------------------------------------------------------------
+ * A3C learner: replaces a3c.Agent's learner graph (agent/a3c.py:11-78) over model/actor_critic.py:3-56 (the same body
+ * as the Ape-X network: attention_CNN || action embedding -> concat 3392 -> actor [256,256,A + softmax] and critic
+ * [256,256,1]) and optimizer/a2c.py:3-26, with TF1 Adam + polynomial decay + global-norm clipping.  network(s, prev_a)
+ * and network(s', a) run as ONE forward over 2B rows; next_value is stop_gradient, so only the first B rows are
+ * differentiated.  The handle is the Ape-X handle type in A3C mode.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct drl_apex drl_a3c;
+
+typedef struct drl_a3c_config {
+  int32_t batch;              /* transitions per step: trajectory (config.json:36) -- the learner trains on one unroll */
+  int32_t height, width, channels; /* 84,84,4                                                           */
+  int32_t num_action;
+  float discount_factor;      /* agent/a3c.py:45                                                        */
+  float start_learning_rate;  /* agent/a3c.py:76                                                        */
+  float end_learning_rate;
+  double learning_frame;
+  float baseline_loss_coef;   /* agent/a3c.py:73                                                        */
+  float entropy_coef;
+  float gradient_clip_norm;   /* agent/a3c.py:79                                                        */
+  int32_t reward_clipping;    /* DRL_REWARD_ABS_ONE / DRL_REWARD_SOFT_ASYMMETRIC (agent/a3c.py:38-43)    */
+  int32_t device;
+  int32_t num_slots;
+  int32_t use_cuda_graph;
+  int32_t math_mode;
+} drl_a3c_config;
+
+typedef struct drl_a3c_out {
+  float pi_loss;        /* -mean(advantage * pi(a))           (optimizer/a2c.py:17-26) */
+  float baseline_loss;  /* mean((r + gamma V(s') - V(s))^2)    (optimizer/a2c.py:9-15)  */
+  float entropy;        /* -mean(sum_a -pi log pi)             (optimizer/a2c.py:3-7)   */
+  float learning_rate;
+  float grad_norm;
+  int64_t step;
+} drl_a3c_out;
+
+int drl_a3c_create(const drl_a3c_config* cfg, drl_a3c** out);
+int drl_a3c_destroy(drl_a3c* h);
+int drl_a3c_param_count(const drl_a3c* h, int64_t* n);
+/* Flat float32 vector, TF variable order of scope {model}/a3c: conv2d x3, dense x2 (embedding), dense x3 (actor),
+ * dense x3 (critic). */
+int drl_a3c_set_params(drl_a3c* h, const float* host_flat, int64_t n);
+int drl_a3c_get_params(drl_a3c* h, float* host_flat, int64_t n);
+int drl_a3c_set_opt_state(drl_a3c* h, const float* host_m, const float* host_v, int64_t n, int64_t step,
+                          float beta1_power, float beta2_power);
+int drl_a3c_get_opt_state(drl_a3c* h, float* host_m, float* host_v, int64_t n, int64_t* step, float* beta1_power,
+                          float* beta2_power);
+int drl_a3c_get_grads(drl_a3c* h, float* host_flat, int64_t n);
+/* Feed of Agent.train (agent/a3c.py:85-103): state, next_state u8 [B,H,W,C]; previous_action, action i32 [B] (the
+ * reference feeds `action` as the next step's previous action, :99); reward f32 [B]; done u8/bool [B]. */
+int drl_a3c_stage(drl_a3c* h, int32_t slot, const uint8_t* state, const uint8_t* next_state,
+                  const int32_t* previous_action, const int32_t* action, const float* reward, const uint8_t* done);
+/* sess.run([pi_loss, baseline_loss, entropy, learning_rate, train_op]) (agent/a3c.py:89-103). */
+int drl_a3c_step(drl_a3c* h, int32_t slot, drl_a3c_out* out);
+int drl_a3c_step_async(drl_a3c* h, int32_t slot);
+int drl_a3c_wait(drl_a3c* h, drl_a3c_out* out);
+/* Agent.get_policy_and_action without the sampling (agent/a3c.py:109-119): policy [n,A] and value [n], n <= 2*batch. */
+int drl_a3c_act(drl_a3c* h, int32_t n, const uint8_t* state, const int32_t* previous_action, float* policy,
+                float* value);
+/* Parity taps of the most recent step: policy [B,A], value [B], next_value [B], advantage [B]. */
+int drl_a3c_taps(drl_a3c* h, float* policy, float* value, float* next_value, float* advantage);
+int drl_a3c_read_buffer(drl_a3c* h, const char* name, float* host_dst, int64_t n);
+int drl_a3c_profile_step(drl_a3c* h, int32_t slot, char* names, int64_t names_len, float* ms, int32_t max_kernels,
+                         int32_t* count);
+int drl_a3c_stream(drl_a3c* h, void** stream);
+int drl_a3c_launches_per_step(const drl_a3c* h, int32_t* n);
+
 #ifdef __cplusplus
 }
 #endif
