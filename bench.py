@@ -494,7 +494,7 @@ def main():
     ap.add_argument("--collective", choices=["peer", "nccl", "none"], default="peer",
                     help="N > 1: fused peer-memory gradient exchange (default) or NCCL all_reduce; 'none' = no "
                          "exchange at all (diagnostic: N independent replicas, NOT a valid data-parallel step)")
-    ap.add_argument("--workload", choices=["impala", "apex", "r2d2"], default="impala",
+    ap.add_argument("--workload", choices=["impala", "apex", "r2d2", "a3c"], default="impala",
                     help="impala = the headline IMPALA learner step (default); apex = the Ape-X DQN learner step "
                          "(BASELINE configs[3], tools/bench_apex.py); r2d2 = the R2D2 learner step (configs[4], "
                          "tools/bench_r2d2.py)")
