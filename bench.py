@@ -254,7 +254,13 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    saved_stdout = None
     if world > 1:
+        # libraries write to fd 1 behind Python's back (NCCL prints "NCCL version ..." there when the image sets
+        # NCCL_DEBUG=VERSION): keep stdout for the ONE JSON line by pointing fd 1 at stderr until that line is printed
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -418,7 +424,10 @@ def run_ours(args):
                 "gpu_launches": launches, "clocks": clocks,
                 "last_step": {k: out[k] for k in ("pi_loss", "baseline_loss", "entropy", "grad_norm", "step")}}
         line.update(line_extra)
-        print(json.dumps(line))
+        if saved_stdout is not None:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
