@@ -332,20 +332,6 @@ int adam_step(cudaStream_t s, const AdamState& o) {
 // Forward of the dueling network (model/apex_value.py:22-41) over M rows.  `tgt` only selects the profile names.
 // Weight images (tensor-core modes): img[1]/img[2] conv2/conv3 forward, img[5]/img[6] the dCol operands of backward.
 // ------------------------------------------------------------------------------------------
-static int fork_to_side(const Streams& st, int i) {
-  if (!st.par) return DRL_OK;
-  DRL_CUDA_CHECK(cudaEventRecord(st.ev[i], st.main));
-  DRL_CUDA_CHECK(cudaStreamWaitEvent(st.side, st.ev[i], 0));
-  pdl_break(st.side);
-  return DRL_OK;
-}
-static int join_from_side(const Streams& st, int i) {
-  if (!st.par) return DRL_OK;
-  DRL_CUDA_CHECK(cudaEventRecord(st.ev[i], st.side));
-  DRL_CUDA_CHECK(cudaStreamWaitEvent(st.main, st.ev[i], 0));
-  pdl_break(st.main);
-  return DRL_OK;
-}
 
 static int apex_forward(const Streams& st, const ApexLayout& pl, const float* P, const WeightImages& wi,
                         const uint8_t* frames, const int32_t* pa, const ApexActs& act, int M, int mode,

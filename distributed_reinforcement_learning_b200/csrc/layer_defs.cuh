@@ -119,4 +119,22 @@ static SplitPlan plan_conv3_wgrad(int Mb, int mode) {
   return mode >= 2 ? plan_split(Mb * 49, 5, 32, 2) : plan_split(Mb * 49, cdiv(576, CfgBig::BM), 16, 2);
 }
 
+// Fork/join helpers: kernels that are off the critical path (the action-embedding table in the forward, every
+// weight gradient except conv1's in the backward) run on the side stream so they fill SMs the critical
+// dgrad chain leaves idle.  Inside CUDA-graph capture the event record/wait pairs become graph edges.
+static inline int fork_to_side(const Streams& st, int i) {
+  if (!st.par) return DRL_OK;
+  DRL_CUDA_CHECK(cudaEventRecord(st.ev[i], st.main));
+  DRL_CUDA_CHECK(cudaStreamWaitEvent(st.side, st.ev[i], 0));
+  pdl_break(st.side);   // the next side-stream kernel depends on a kernel of another stream: full dependency
+  return DRL_OK;
+}
+static inline int join_from_side(const Streams& st, int i) {
+  if (!st.par) return DRL_OK;
+  DRL_CUDA_CHECK(cudaEventRecord(st.ev[i], st.side));
+  DRL_CUDA_CHECK(cudaStreamWaitEvent(st.main, st.ev[i], 0));
+  pdl_break(st.main);
+  return DRL_OK;
+}
+
 }  // namespace drl

@@ -72,24 +72,6 @@ int net_retile(cudaStream_t, cudaStream_t s_rest, const ParamLayout& pl, const f
   return DRL_OK;
 }
 
-// Fork/join helpers: kernels that are off the critical path (the action-embedding table in the forward, every
-// weight gradient except conv1's in the backward) run on the side stream so they fill SMs the critical
-// dgrad chain leaves idle.  Inside CUDA-graph capture the event record/wait pairs become graph edges.
-static int fork_to_side(const Streams& st, int i) {
-  if (!st.par) return DRL_OK;
-  DRL_CUDA_CHECK(cudaEventRecord(st.ev[i], st.main));
-  DRL_CUDA_CHECK(cudaStreamWaitEvent(st.side, st.ev[i], 0));
-  pdl_break(st.side);   // the next side-stream kernel depends on a kernel of another stream: full dependency
-  return DRL_OK;
-}
-static int join_from_side(const Streams& st, int i) {
-  if (!st.par) return DRL_OK;
-  DRL_CUDA_CHECK(cudaEventRecord(st.ev[i], st.side));
-  DRL_CUDA_CHECK(cudaStreamWaitEvent(st.main, st.ev[i], 0));
-  pdl_break(st.main);
-  return DRL_OK;
-}
-
 int net_forward(const Streams& st, const ParamLayout& pl, const float* P, const WeightImages& wi, const Inputs& in,
                 const Acts& act, int B, int T, int mode, bool retile) {
   const int M = B * T;

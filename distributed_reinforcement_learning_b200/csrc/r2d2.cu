@@ -408,20 +408,6 @@ __global__ void __launch_bounds__(256) r2d2_td_kernel(R2TdArgs a) {
   }
 }
 
-static int fork_to_side(const Streams& st, int i) {
-  if (!st.par) return DRL_OK;
-  DRL_CUDA_CHECK(cudaEventRecord(st.ev[i], st.main));
-  DRL_CUDA_CHECK(cudaStreamWaitEvent(st.side, st.ev[i], 0));
-  pdl_break(st.side);
-  return DRL_OK;
-}
-static int join_from_side(const Streams& st, int i) {
-  if (!st.par) return DRL_OK;
-  DRL_CUDA_CHECK(cudaEventRecord(st.ev[i], st.side));
-  DRL_CUDA_CHECK(cudaStreamWaitEvent(st.main, st.ev[i], 0));
-  pdl_break(st.main);
-  return DRL_OK;
-}
 
 constexpr size_t kR2FwdSmem = 0, kR2BwdSmem = 0;     // the recurrence kernels only use small static shared arrays
 

@@ -201,3 +201,39 @@ def test_apex_agent_surface_and_no_cpu_fallback(native, tmp_path):
         with pytest.raises(native.DrlError) as ei:
             ag.distributed_train(*[b[k] for k in ax.TRAIN_FIELDS])
         assert "no CPU fallback" in str(ei.value)
+
+
+def test_native_per_random_op_sequences(native):
+    """Property test (hypothesis): arbitrary interleavings of add / sample / update keep the native sum tree
+    bit-identical to the NumPy restatement (totals, sampled leaves, priorities) for arbitrary capacities."""
+    from hypothesis import given, settings, strategies as st
+    from distributed_reinforcement_learning_b200.distributed_queue import buffer_queue as bq
+
+    ops = st.lists(st.tuples(st.sampled_from(["add", "add", "sample", "update"]),
+                             st.floats(min_value=0.0, max_value=50.0, allow_nan=False),
+                             st.floats(min_value=0.0, max_value=0.999999)), min_size=1, max_size=60)
+
+    @settings(max_examples=40, deadline=None)
+    @given(cap=st.integers(min_value=2, max_value=33), seq=ops)
+    def run(cap, seq):
+        ref, mem = per_np.MemoryNP(cap), bq.Memory(cap)
+        last = None
+        for kind, err, u in seq:
+            if kind == "add":
+                ref.add(err)
+                mem.add(err, None)
+            elif kind == "sample" and ref.tree.n_entries > 0 and ref.tree.total() > 0:
+                n = 1 + int(u * 4)
+                us = [(u * (i + 1)) % 1.0 for i in range(n)]
+                ri, rd, rp, rw = ref.sample(n, us)
+                _, idxs, w = mem.sample(n, us)
+                assert idxs == list(ri) and np.array_equal(mem.last_priorities, rp)
+                assert w == pytest.approx(rw, rel=1e-12)
+                last = idxs
+            elif kind == "update" and last:
+                k = last[int(u * len(last)) % len(last)]
+                ref.update(k, err)
+                mem.update(k, err)
+            assert mem.tree.total() == ref.tree.total()
+        mem.tree.close()
+    run()
