@@ -147,6 +147,9 @@ def _load():
         "drl_apex_stage": (C.c_int, [vp, i32] + [vp] * 7),
         "drl_apex_step": (C.c_int, [vp, i32, C.POINTER(ApexOut), vp]),
         "drl_apex_step_async": (C.c_int, [vp, i32]),
+        "drl_apex_forward_backward": (C.c_int, [vp, i32]),
+        "drl_apex_grad_bucket": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i64)]),
+        "drl_apex_apply": (C.c_int, [vp, f32]),
         "drl_apex_wait": (C.c_int, [vp, C.POINTER(ApexOut), vp]),
         "drl_apex_td_error": (C.c_int, [vp, i32] + [vp] * 7),
         "drl_apex_act": (C.c_int, [vp, i32, vp, vp, vp]),
@@ -167,6 +170,9 @@ def _load():
         "drl_a3c_stage": (C.c_int, [vp, i32] + [vp] * 6),
         "drl_a3c_step": (C.c_int, [vp, i32, C.POINTER(A3cOut)]),
         "drl_a3c_step_async": (C.c_int, [vp, i32]),
+        "drl_a3c_forward_backward": (C.c_int, [vp, i32]),
+        "drl_a3c_grad_bucket": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i64)]),
+        "drl_a3c_apply": (C.c_int, [vp, f32]),
         "drl_a3c_wait": (C.c_int, [vp, C.POINTER(A3cOut)]),
         "drl_a3c_act": (C.c_int, [vp, i32, vp, vp, vp, vp]),
         "drl_a3c_taps": (C.c_int, [vp] * 5),
@@ -186,6 +192,9 @@ def _load():
         "drl_r2d2_stage": (C.c_int, [vp, i32] + [vp] * 8),
         "drl_r2d2_step": (C.c_int, [vp, i32, C.POINTER(R2d2Out), vp]),
         "drl_r2d2_step_async": (C.c_int, [vp, i32]),
+        "drl_r2d2_forward_backward": (C.c_int, [vp, i32]),
+        "drl_r2d2_grad_bucket": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i64)]),
+        "drl_r2d2_apply": (C.c_int, [vp, f32]),
         "drl_r2d2_wait": (C.c_int, [vp, C.POINTER(R2d2Out), vp]),
         "drl_r2d2_td_error": (C.c_int, [vp, i32] + [vp] * 8),
         "drl_r2d2_act": (C.c_int, [vp, i32] + [vp] * 7),

@@ -5,6 +5,7 @@ import ctypes as C
 import numpy as np
 
 from . import _native as N
+from . import dp
 from .apex_learner import _as_u8
 
 
@@ -29,6 +30,7 @@ class NativeA3CLearner:
         self.param_count = int(n.value)
         self.num_slots = int(num_slots)
         self._keep = [None] * self.num_slots
+        self._dp = dp.BucketAllReduce("a3c", self._h, int(device))
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -78,8 +80,12 @@ class NativeA3CLearner:
         N.check(N.lib.drl_a3c_stage(self._h, slot, *[N.ptr(a) for a in arrs]))
 
     def step(self, slot=0):
+        if dp.distributed():
+            self._dp.step_async(slot)           # data parallel: see dp.py
+        else:
+            N.check(N.lib.drl_a3c_step_async(self._h, slot))
         o = N.A3cOut()
-        N.check(N.lib.drl_a3c_step(self._h, slot, C.byref(o)))
+        N.check(N.lib.drl_a3c_wait(self._h, C.byref(o)))
         return dict(pi_loss=o.pi_loss, baseline_loss=o.baseline_loss, entropy=o.entropy, learning_rate=o.learning_rate,
                     grad_norm=o.grad_norm, step=o.step)
 

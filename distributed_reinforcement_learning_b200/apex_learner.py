@@ -10,6 +10,7 @@ import ctypes as C
 import numpy as np
 
 from . import _native as N
+from . import dp
 
 MAIN, TARGET = 0, 1
 
@@ -41,6 +42,7 @@ class NativeApexLearner:
         self.param_count = int(n.value)
         self.num_slots = int(num_slots)
         self._keep = [None] * self.num_slots
+        self._dp = dp.BucketAllReduce("apex", self._h, self.device)
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -106,14 +108,16 @@ class NativeApexLearner:
         return dict(loss=o.loss, learning_rate=o.learning_rate, grad_norm=o.grad_norm, step=o.step)
 
     def step(self, slot=0):
-        """-> (scalars dict, td_error [B]) of agent/apex.py:139-151."""
-        o = N.ApexOut()
-        td = np.empty(self.B, np.float32)
-        N.check(N.lib.drl_apex_step(self._h, slot, C.byref(o), N.ptr(td)))
-        return self._out(o), td
+        """-> (scalars dict, td_error [B]) of agent/apex.py:139-151.  With torch.distributed initialised (world > 1) the
+        step is data parallel: see dp.py."""
+        self.step_async(slot)
+        return self.wait()
 
     def step_async(self, slot=0):
-        N.check(N.lib.drl_apex_step_async(self._h, slot))
+        if dp.distributed():
+            self._dp.step_async(slot)
+        else:
+            N.check(N.lib.drl_apex_step_async(self._h, slot))
 
     def wait(self):
         o = N.ApexOut()

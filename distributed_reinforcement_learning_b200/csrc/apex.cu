@@ -292,11 +292,11 @@ __global__ void __launch_bounds__(256) adam_apply_kernel(AdamState o) {
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) s += red[i];
-    const float norm = sqrtf(s);
-    s_scale = (o.clip_norm > 0.f) ? o.clip_norm * fminf(1.0f / norm, 1.0f / o.clip_norm) : 1.0f;
+    const float norm = sqrtf(s) * o.grad_scale;
+    s_scale = ((o.clip_norm > 0.f) ? o.clip_norm * fminf(1.0f / norm, 1.0f / o.clip_norm) : 1.0f) * o.grad_scale;
     if (blockIdx.x == 0) {
-      o.out[0] = o.loss[0]; o.out[1] = *o.lr_cur; o.out[2] = norm;
-      o.out[3] = o.loss[1]; o.out[4] = o.loss[2];          // A3C: baseline loss, entropy (zero for the DQN learners)
+      o.out[0] = o.loss[0] * o.grad_scale; o.out[1] = *o.lr_cur; o.out[2] = norm;
+      o.out[3] = o.loss[1] * o.grad_scale; o.out[4] = o.loss[2] * o.grad_scale;          // A3C: baseline loss, entropy (zero for the DQN learners)
       const long long st = *o.step;
       o.out[6] = __int_as_float((int)(st & 0xffffffffll));
       o.out[7] = __int_as_float((int)(st >> 32));
@@ -790,6 +790,36 @@ int run_step(drl_apex* h, int slot) {
   return DRL_OK;
 }
 
+// data parallel: the step in two halves around the caller's all-reduce of the bucket (eager launches)
+int run_forward_backward(drl_apex* h, int slot) {
+  ApexSlot& sl = h->slots[slot];
+  if (!sl.has_data) { set_error("slot %d has not been staged", slot); return DRL_ERR_STATE; }
+  DRL_CUDA_CHECK(cudaStreamWaitEvent(h->compute, sl.staged, 0));
+  DRL_CUDA_CHECK(cudaEventRecord(h->ev_start, h->compute));
+  h->main_images_stale = true;
+  int cnt = 0;
+  DRL_TRY(enqueue_forward_td(h, sl, h->B, true, h->d_td + (size_t)slot * h->B, &cnt));
+  DRL_TRY(apex_backward(streams_of(h), h->pl, h->params, h->wi, h->grads, sl.frames, sl.pa2, h->act, h->bwd, 2 * h->B, h->B,
+                        h->mode, &cnt));
+  h->launches = cnt + 2;
+  h->last_n = h->B;
+  h->last_slot = slot;
+  DRL_CUDA_CHECK(cudaEventRecord(sl.consumed, h->compute));
+  return DRL_OK;
+}
+int run_apply(drl_apex* h, float grad_scale) {
+  pdl_break(h->compute);
+  AdamState o = h->opt;
+  o.out = h->d_out + 8 * h->last_slot;
+  o.grad_scale = grad_scale;
+  DRL_TRY(adam_step(h->compute, o));
+  h->main_images_stale = true;
+  DRL_CUDA_CHECK(cudaEventRecord(h->ev_stop, h->compute));
+  DRL_CUDA_CHECK(cudaEventRecord(h->ev_done, h->compute));
+  h->pending = true;
+  return DRL_OK;
+}
+
 int stage_into(drl_apex* h, ApexSlot& s, cudaStream_t stream, int n, int row2, const uint8_t* state,
                const uint8_t* next_state, const int32_t* previous_action, const int32_t* action, const float* reward,
                const uint8_t* done, const float* is_weight) {
@@ -878,7 +908,7 @@ int drl_apex_create(const drl_apex_config* cfg, drl_apex** out) {
     DRL_TRY(dev_alloc(h, &h->target_value, B));
     DRL_TRY(dev_alloc(h, &h->sav, B));
     DRL_TRY(dev_alloc(h, &h->td_dev, B));
-    DRL_TRY(dev_alloc(h, &h->loss, 4));
+    h->loss = h->grads + NP;     // the loss scalars ride in the tail of the gradient bucket (one all-reduce covers both)
     DRL_TRY(dev_alloc(h, &h->adv, B));
     DRL_TRY(dev_alloc(h, &h->d_step, 1));
     DRL_TRY(dev_alloc(h, &h->d_lr, 1));
@@ -908,6 +938,7 @@ int drl_apex_create(const drl_apex_config* cfg, drl_apex** out) {
     o.out = h->d_out; o.loss = h->loss;
     o.start_lr = cfg->start_learning_rate; o.end_lr = cfg->end_learning_rate; o.learning_frame = cfg->learning_frame;
     o.clip_norm = cfg->gradient_clip_norm;
+    o.grad_scale = 1.0f;
     h->slots.resize(ns + 1);
     h->graph_step.assign(ns, nullptr);
     for (ApexSlot& s : h->slots) {
@@ -1060,6 +1091,25 @@ int drl_apex_step_async(drl_apex* h, int32_t slot) {
   if (slot < 0 || slot >= h->cfg.num_slots) { set_error("slot %d out of range", slot); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
   return run_step(h, slot);
+}
+
+int drl_apex_forward_backward(drl_apex* h, int32_t slot) {
+  DRL_TRY(check_handle(h));
+  if (slot < 0 || slot >= h->cfg.num_slots) { set_error("slot %d out of range", slot); return DRL_ERR_INVALID; }
+  DRL_TRY(set_device(h));
+  return run_forward_backward(h, slot);
+}
+int drl_apex_grad_bucket(drl_apex* h, void** dev_ptr, int64_t* count) {
+  DRL_TRY(check_handle(h));
+  if (dev_ptr) *dev_ptr = h->grads;
+  if (count) *count = h->pl.padded_total + 4;
+  return DRL_OK;
+}
+int drl_apex_apply(drl_apex* h, float grad_scale) {
+  DRL_TRY(check_handle(h));
+  if (!(grad_scale > 0.f)) { set_error("apply: grad_scale must be > 0"); return DRL_ERR_INVALID; }
+  DRL_TRY(set_device(h));
+  return run_apply(h, grad_scale);
 }
 
 int drl_apex_wait(drl_apex* h, drl_apex_out* out, float* td_error) {
@@ -1273,6 +1323,9 @@ int drl_a3c_step_async(drl_a3c* h, int32_t slot) {
   if (h->algo != 1) { set_error("not an A3C handle"); return DRL_ERR_INVALID; }
   return drl_apex_step_async(h, slot);
 }
+int drl_a3c_forward_backward(drl_a3c* h, int32_t slot) { return drl_apex_forward_backward(h, slot); }
+int drl_a3c_grad_bucket(drl_a3c* h, void** dev_ptr, int64_t* count) { return drl_apex_grad_bucket(h, dev_ptr, count); }
+int drl_a3c_apply(drl_a3c* h, float grad_scale) { return drl_apex_apply(h, grad_scale); }
 int drl_a3c_wait(drl_a3c* h, drl_a3c_out* out) {
   DRL_TRY(check_handle(h));
   drl_apex_out o{};

@@ -183,6 +183,8 @@ struct AdamState {
   float* out;               // [8] mapped pinned: loss, lr, grad_norm, -, -, -, step_lo, step_hi
   const float* loss;
   float start_lr, end_lr; double learning_frame; float clip_norm;
+  float grad_scale;         // data parallel: the bucket holds the SUM over ranks of per-rank MEAN-loss gradients -> 1/world
+                            // (1 for a single replica); applied to the gradient, its norm and the logged losses
 };
 int adam_step(cudaStream_t s, const AdamState& o);   // 2 launches: partial norms + scalars, then the update
 

@@ -852,6 +852,35 @@ int run_step(drl_r2d2* h, int slot) {
   return DRL_OK;
 }
 
+// data parallel: the step in two halves around the caller's all-reduce of the bucket (eager launches)
+int run_forward_backward(drl_r2d2* h, int slot) {
+  R2Slot& sl = h->slots[slot];
+  if (!sl.has_data) { set_error("slot %d has not been staged", slot); return DRL_ERR_STATE; }
+  DRL_CUDA_CHECK(cudaStreamWaitEvent(h->compute, sl.staged, 0));
+  DRL_CUDA_CHECK(cudaEventRecord(h->ev_start, h->compute));
+  h->main_images_stale = true;
+  int cnt = 0;
+  DRL_TRY(enqueue_forward_td(h, sl.in, h->B, true, h->d_td + (size_t)slot * h->B, &cnt));
+  DRL_TRY(r2_backward(streams_of(h), h->pl, h->params, h->wi, h->grads, sl.in, h->act, h->bwd, h->B, h->S, h->mode, &cnt));
+  h->launches = cnt + 2;
+  h->last_b = h->B;
+  h->last_slot = slot;
+  DRL_CUDA_CHECK(cudaEventRecord(sl.consumed, h->compute));
+  return DRL_OK;
+}
+int run_apply(drl_r2d2* h, float grad_scale) {
+  pdl_break(h->compute);
+  AdamState o = h->opt;
+  o.out = h->d_out + 8 * h->last_slot;
+  o.grad_scale = grad_scale;
+  DRL_TRY(adam_step(h->compute, o));
+  h->main_images_stale = true;
+  DRL_CUDA_CHECK(cudaEventRecord(h->ev_stop, h->compute));
+  DRL_CUDA_CHECK(cudaEventRecord(h->ev_done, h->compute));
+  h->pending = true;
+  return DRL_OK;
+}
+
 // H2D of nb sequences into slot s on `stream` (fields that are null are skipped)
 int stage_into(drl_r2d2* h, R2Slot& s, cudaStream_t stream, int nb, int steps, const uint8_t* state,
                const int32_t* previous_action, const int32_t* action, const float* h0, const float* c0, const float* reward,
@@ -948,7 +977,7 @@ int drl_r2d2_create(const drl_r2d2_config* cfg, drl_r2d2** out) {
     DRL_TRY(dev_alloc(h, &h->sav, B * Nt));
     DRL_TRY(dev_alloc(h, &h->target_value, B * Nt));
     DRL_TRY(dev_alloc(h, &h->td_dev, B));
-    DRL_TRY(dev_alloc(h, &h->loss, 4));
+    h->loss = h->grads + NP;     // loss scalar in the tail of the gradient bucket (one all-reduce covers both)
     DRL_TRY(dev_alloc(h, &h->c_last, M * kR2L));
     DRL_TRY(dev_alloc(h, &h->d_step, 1));
     DRL_TRY(dev_alloc(h, &h->d_lr, 1));
@@ -978,6 +1007,7 @@ int drl_r2d2_create(const drl_r2d2_config* cfg, drl_r2d2** out) {
     o.out = h->d_out; o.loss = h->loss;
     o.start_lr = cfg->learning_rate; o.end_lr = cfg->learning_rate; o.learning_frame = 1.0;   // constant (agent/r2d2.py:91)
     o.clip_norm = 0.0f;                                                                        // minimize(): no clipping
+    o.grad_scale = 1.0f;
     h->slots.resize(ns + 1);
     h->graph_step.assign(ns, nullptr);
     for (R2Slot& s : h->slots) {
@@ -1132,6 +1162,24 @@ int drl_r2d2_step_async(drl_r2d2* h, int32_t slot) {
   if (slot < 0 || slot >= h->cfg.num_slots) { set_error("slot %d out of range", slot); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
   return run_step(h, slot);
+}
+int drl_r2d2_forward_backward(drl_r2d2* h, int32_t slot) {
+  DRL_TRY(check_handle(h));
+  if (slot < 0 || slot >= h->cfg.num_slots) { set_error("slot %d out of range", slot); return DRL_ERR_INVALID; }
+  DRL_TRY(set_device(h));
+  return run_forward_backward(h, slot);
+}
+int drl_r2d2_grad_bucket(drl_r2d2* h, void** dev_ptr, int64_t* count) {
+  DRL_TRY(check_handle(h));
+  if (dev_ptr) *dev_ptr = h->grads;
+  if (count) *count = h->pl.padded_total + 4;
+  return DRL_OK;
+}
+int drl_r2d2_apply(drl_r2d2* h, float grad_scale) {
+  DRL_TRY(check_handle(h));
+  if (!(grad_scale > 0.f)) { set_error("apply: grad_scale must be > 0"); return DRL_ERR_INVALID; }
+  DRL_TRY(set_device(h));
+  return run_apply(h, grad_scale);
 }
 int drl_r2d2_wait(drl_r2d2* h, drl_r2d2_out* out, float* td_error) {
   DRL_TRY(check_handle(h));

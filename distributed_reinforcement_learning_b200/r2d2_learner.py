@@ -10,6 +10,7 @@ import ctypes as C
 import numpy as np
 
 from . import _native as N
+from . import dp
 
 MAIN, TARGET = 0, 1
 
@@ -38,6 +39,7 @@ class NativeR2D2Learner:
         self.param_count = int(n.value)
         self.num_slots = int(num_slots)
         self._keep = [None] * self.num_slots
+        self._dp = dp.BucketAllReduce("r2d2", self._h, self.device)
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -99,13 +101,14 @@ class NativeR2D2Learner:
         return dict(loss=o.loss, grad_norm=o.grad_norm, step=o.step)
 
     def step(self, slot=0):
-        o = N.R2d2Out()
-        td = np.empty(self.B, np.float32)
-        N.check(N.lib.drl_r2d2_step(self._h, slot, C.byref(o), N.ptr(td)))
-        return self._out(o), td
+        self.step_async(slot)
+        return self.wait()
 
     def step_async(self, slot=0):
-        N.check(N.lib.drl_r2d2_step_async(self._h, slot))
+        if dp.distributed():
+            self._dp.step_async(slot)           # data parallel: see dp.py
+        else:
+            N.check(N.lib.drl_r2d2_step_async(self._h, slot))
 
     def wait(self):
         o = N.R2d2Out()

@@ -326,6 +326,13 @@ int drl_apex_stage(drl_apex* h, int32_t slot, const uint8_t* state, const uint8_
 int drl_apex_step(drl_apex* h, int32_t slot, drl_apex_out* out, float* td_error);
 int drl_apex_step_async(drl_apex* h, int32_t slot);
 int drl_apex_wait(drl_apex* h, drl_apex_out* out, float* td_error);
+/* (new) Data-parallel step in two halves (one process per GPU, each rank feeds its own B transitions): forward + TD +
+ * backward into the gradient bucket [padded grads | loss scalars] -> the CALLER all-reduces (SUM) the bucket on the
+ * learner's stream (drl_apex_stream) -> clip + Adam on bucket * grad_scale.  value_loss is a batch MEAN
+ * (agent/apex.py:65), so grad_scale = 1 / world_size makes the update that of the undivided global batch. */
+int drl_apex_forward_backward(drl_apex* h, int32_t slot);
+int drl_apex_grad_bucket(drl_apex* h, void** dev_ptr, int64_t* count);
+int drl_apex_apply(drl_apex* h, float grad_scale);   /* async; follow with drl_apex_wait */
 /* Agent.get_td_error (agent/apex.py:116-133): forward only, n <= batch transitions -> |target - q(s,a)| [n]. */
 int drl_apex_td_error(drl_apex* h, int32_t n, const uint8_t* state, const uint8_t* next_state,
                       const int32_t* previous_action, const int32_t* action, const float* reward,
@@ -428,6 +435,11 @@ int drl_r2d2_stage(drl_r2d2* h, int32_t slot, const uint8_t* state, const int32_
 int drl_r2d2_step(drl_r2d2* h, int32_t slot, drl_r2d2_out* out, float* td_error);
 int drl_r2d2_step_async(drl_r2d2* h, int32_t slot);
 int drl_r2d2_wait(drl_r2d2* h, drl_r2d2_out* out, float* td_error);
+/* (new) Data-parallel halves, as drl_apex_forward_backward / _grad_bucket / _apply (value_loss is a batch mean,
+ * agent/r2d2.py:90: grad_scale = 1 / world_size). */
+int drl_r2d2_forward_backward(drl_r2d2* h, int32_t slot);
+int drl_r2d2_grad_bucket(drl_r2d2* h, void** dev_ptr, int64_t* count);
+int drl_r2d2_apply(drl_r2d2* h, float grad_scale);
 /* Agent.get_td_error (agent/r2d2.py:97-130) for n <= batch sequences at once: td_error[i] = |mean(target - q)| of
  * sequence i (the reference calls it with one sequence). */
 int drl_r2d2_td_error(drl_r2d2* h, int32_t n, const uint8_t* state, const int32_t* previous_action,
@@ -505,6 +517,10 @@ int drl_a3c_stage(drl_a3c* h, int32_t slot, const uint8_t* state, const uint8_t*
 int drl_a3c_step(drl_a3c* h, int32_t slot, drl_a3c_out* out);
 int drl_a3c_step_async(drl_a3c* h, int32_t slot);
 int drl_a3c_wait(drl_a3c* h, drl_a3c_out* out);
+/* (new) Data-parallel halves (all three A2C losses are batch means: grad_scale = 1 / world_size). */
+int drl_a3c_forward_backward(drl_a3c* h, int32_t slot);
+int drl_a3c_grad_bucket(drl_a3c* h, void** dev_ptr, int64_t* count);
+int drl_a3c_apply(drl_a3c* h, float grad_scale);
 /* Agent.get_policy_and_action without the sampling (agent/a3c.py:109-119): policy [n,A] and value [n], n <= 2*batch. */
 int drl_a3c_act(drl_a3c* h, int32_t n, const uint8_t* state, const int32_t* previous_action, float* policy,
                 float* value);

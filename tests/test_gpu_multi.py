@@ -98,3 +98,105 @@ def test_fused_peer_exchange_equals_nccl_path(native, tmp_path, world):
     assert np.allclose(p0["losses"], n0["losses"], rtol=1e-6) and np.allclose(p0["losses2"], n0["losses2"], rtol=1e-5)
     upd = np.max(np.abs(n0["params2"] - it.flatten_params(parity.make_case(B, T, A, seed=77)[1])))
     assert np.max(np.abs(p0["params2"] - n0["params2"])) <= 1e-4 * upd
+
+
+# ---- data-parallel Ape-X / A3C / R2D2 (distributed_reinforcement_learning_b200/dp.py) -------------------------------
+def _family_case(family):
+    """-> (make engine(B, device), batch dict, stage(eng, batch), per-sample slicer)."""
+    if family == "r2d2":
+        from oracle import r2d2_torch as rt
+        from distributed_reinforcement_learning_b200.r2d2_learner import NativeR2D2Learner
+        kwp = dict(num_action=4, lstm_size=64, input_shape=(84, 84, 1))
+        pm = rt.flatten_params(rt.init_params(0, torch.float32, **kwp))
+        pt = rt.flatten_params(rt.init_params(1, torch.float32, **kwp))
+        batch = rt.make_sequences(4, S=6, seed=31)
+
+        def make(Bn, dev):
+            e = NativeR2D2Learner(batch=Bn, seq_len=6, burn_in=2, device=dev)
+            e.set_params(pm, 0)
+            e.set_params(pt, 1)
+            return e
+
+        def stage(e, b):
+            e.stage(0, b["state"], b["previous_action"], b["action"], b["h"][:, 0], b["c"][:, 0], b["reward"], b["done"],
+                    b["weight"])
+        return make, batch, stage
+    from oracle import apex_torch as ax
+    pm = ax.flatten_params(ax.init_params(0, torch.float32, num_action=4))
+    pt = ax.flatten_params(ax.init_params(1, torch.float32, num_action=4))
+    batch = ax.make_transitions(4, seed=31)
+    if family == "apex":
+        from distributed_reinforcement_learning_b200.apex_learner import NativeApexLearner
+
+        def make(Bn, dev):
+            e = NativeApexLearner(batch=Bn, num_action=4, device=dev)
+            e.set_params(pm, 0)
+            e.set_params(pt, 1)
+            return e
+
+        def stage(e, b):
+            e.stage(0, *[b[k] for k in ax.TRAIN_FIELDS])
+        return make, batch, stage
+    from distributed_reinforcement_learning_b200.a3c_learner import NativeA3CLearner
+
+    def make(Bn, dev):
+        e = NativeA3CLearner(batch=Bn, num_action=4, device=dev)
+        e.set_params(pm)
+        return e
+
+    def stage(e, b):
+        e.stage(0, *[b[k] for k in ax.TRAIN_FIELDS[:-1]])
+    return make, batch, stage
+
+
+def _scalars(out):
+    out = out[0] if isinstance(out, tuple) else out
+    return np.array([out[k] for k in sorted(out) if k not in ("step", "learning_rate")], np.float64)
+
+
+def _family_worker(rank, world, port, out_dir, family):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    make, batch, stage = _family_case(family)
+    n = len(batch["reward"]) // world
+    sh = {k: v[rank * n:(rank + 1) * n] for k, v in batch.items()}
+    eng = make(n, rank)
+    stage(eng, sh)
+    out = eng.step(0)                      # forward_backward -> all_reduce(SUM) -> apply(1 / world)
+    st = eng.get_opt_state()
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), grads=eng.get_grads(), m=st["m"], v=st["v"],
+             params=eng.get_params(), scalars=_scalars(out))
+    dist.barrier()
+    eng.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("family", ["apex", "a3c", "r2d2"])
+def test_two_gpu_mean_loss_learners_equal_single_replica(native, tmp_path, family):
+    """Two ranks with half of the minibatch each (bucket SUM x 1/2, their losses are batch means) reproduce the
+    gradient, the logged scalars and the Adam slots of one replica stepping on the undivided minibatch."""
+    if native.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    mp.spawn(_family_worker, args=(2, _free_port(), str(tmp_path), family), nprocs=2, join=True)
+    r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
+    for k in ("m", "v", "params"):
+        assert np.array_equal(r0[k], r1[k]), k                       # replicas stay identical
+    make, batch, stage = _family_case(family)
+    eng = make(len(batch["reward"]), 0)
+    p0 = eng.get_params()
+    stage(eng, batch)
+    out = eng.step(0)
+    st = eng.get_opt_state()
+    g1, p1 = eng.get_grads(), eng.get_params()
+    eng.close()
+    # the bucket holds the SUM of the two half-batch mean gradients: x 1/2 = the full-batch mean gradient
+    assert parity.rel_err(0.5 * r0["grads"], g1) < parity.TOL
+    assert parity.rel_err(r0["m"], st["m"]) < parity.TOL and parity.rel_err(r0["v"], st["v"]) < 2 * parity.TOL
+    assert np.allclose(r0["scalars"], _scalars(out), rtol=1e-4)
+    # Adam's first step is ~ lr * sign(g): elements with |g| near 1e-8 are ill-conditioned, so compare the bulk
+    d = np.abs((r0["params"] - p0) - (p1 - p0))
+    assert np.quantile(d, 0.999) <= 1e-2 * np.max(np.abs(p1 - p0)) and np.max(d) <= 2.1 * np.max(np.abs(p1 - p0))
