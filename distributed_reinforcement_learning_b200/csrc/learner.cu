@@ -344,7 +344,7 @@ int drl_debug_trace(void* dev_buf) {
   DRL_CUDA_CHECK(cudaDeviceSynchronize());
   return DRL_OK;
 }
-const char* drl_version(void) { return "drl_b200 0.2 (sm_100a; tcgen05 3xTF32 gather-GEMM, FP32-FFMA fallback core, NVLink peer exchange)"; }
+const char* drl_version(void) { return "drl_b200 0.3 (sm_100a; tcgen05 3xTF32 gather-GEMM, FP32-FFMA core, NVLink peer exchange; IMPALA, Ape-X, R2D2, A3C learners)"; }
 
 int drl_device_count(void) {
   int n = 0;

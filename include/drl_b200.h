@@ -1,5 +1,6 @@
 /*
- * drl_b200.h -- C-ABI of the B200-native IMPALA learner hot path.
+ * drl_b200.h -- C-ABI of the B200-native learner hot paths: IMPALA (the headline path), then the Ape-X DQN, R2D2 and
+ * A3C learner steps and the prioritized-replay index.
  *
  * The reference (chagmgang/distributed_reinforcement_learning @ 1890ce4) has no FFI: its hot
  * path is a Python call surface over a TF1 graph.  This header is what a replacement of that
