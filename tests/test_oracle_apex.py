@@ -213,7 +213,7 @@ def test_native_per_random_op_sequences(native):
                              st.floats(min_value=0.0, max_value=50.0, allow_nan=False),
                              st.floats(min_value=0.0, max_value=0.999999)), min_size=1, max_size=60)
 
-    @settings(max_examples=40, deadline=None)
+    @settings(max_examples=60, deadline=None, derandomize=True, database=None)
     @given(cap=st.integers(min_value=2, max_value=33), seq=ops)
     def run(cap, seq):
         ref, mem = per_np.MemoryNP(cap), bq.Memory(cap)
@@ -225,10 +225,14 @@ def test_native_per_random_op_sequences(native):
             elif kind == "sample" and ref.tree.n_entries > 0 and ref.tree.total() > 0:
                 n = 1 + int(u * 4)
                 us = [(u * (i + 1)) % 1.0 for i in range(n)]
-                ri, rd, rp, rw = ref.sample(n, us)
+                with np.errstate(all="ignore"):
+                    ri, rd, rp, rw = ref.sample(n, us)
                 _, idxs, w = mem.sample(n, us)
                 assert idxs == list(ri) and np.array_equal(mem.last_priorities, rp)
-                assert w == pytest.approx(rw, rel=1e-12)
+                # a draw of mass exactly 0 can land on a still-empty leaf (priority 0): the reference then yields
+                # inf / inf = nan weights, and so do both implementations here
+                with np.errstate(all="ignore"):
+                    assert np.allclose(w, rw, rtol=1e-12, atol=0.0, equal_nan=True)
                 last = idxs
             elif kind == "update" and last:
                 k = last[int(u * len(last)) % len(last)]
