@@ -13,6 +13,7 @@ Same constructor arguments, method names and ``batch_tuple`` field order as the 
 """
 import collections
 import ctypes as C
+import threading
 
 import numpy as np
 
@@ -186,3 +187,171 @@ class Memory(object):
 
     def update(self, idx, error):
         N.check(N.lib.drl_per_update(self.tree._p, int(idx), float(error)))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Host-side transport and actor-side buffers of the other launchers (train_apex.py, train_r2d2.py, train_a3c.py).
+# The reference moves these records between processes through a shared ``tf.FIFOQueue`` on the learner's gRPC server;
+# that control plane is out of scope here.  What follows keeps the call surface inside ONE
+# process -- a bounded, blocking, thread-safe FIFO of fixed-field records -- so that the learner loops and
+# actor threads of the launchers can run against the GPU learners unchanged.
+# ---------------------------------------------------------------------------------------------------------------
+class _RecordFIFO:
+    """Bounded FIFO of records with named fields; ``put`` blocks while full, ``get`` while empty (tf.FIFOQueue semantics)."""
+
+    def __init__(self, fields, capacity, shapes=None):
+        self.fields = tuple(fields)
+        self.capacity = int(capacity)
+        self.shapes = shapes or {}
+        self._items = collections.deque()
+        self._cv = threading.Condition()
+        self.tuple_type = collections.namedtuple('batch_tuple', self.fields)
+
+    def put(self, record, timeout=None):
+        for name, shape in self.shapes.items():
+            got = tuple(np.shape(record[name]))
+            if got != tuple(shape):
+                raise ValueError("%s: expected shape %s, got %s" % (name, tuple(shape), got))   # static placeholder shapes
+        with self._cv:
+            if not self._cv.wait_for(lambda: len(self._items) < self.capacity, timeout):
+                raise N.TimeoutError_(N.DRL_ERR_TIMEOUT, "queue full")
+            self._items.append(tuple(record[f] for f in self.fields))
+            self._cv.notify_all()
+
+    def get_many(self, n, timeout=None):
+        out = []
+        with self._cv:
+            for _ in range(n):
+                if not self._cv.wait_for(lambda: len(self._items) > 0, timeout):
+                    raise N.TimeoutError_(N.DRL_ERR_TIMEOUT, "queue empty")
+                out.append(self._items.popleft())
+                self._cv.notify_all()
+        return self.tuple_type(*[[rec[i] for rec in out] for i in range(len(self.fields))])
+
+    def size(self):
+        with self._cv:
+            return len(self._items)
+
+
+class _QueueBase:
+    _FIELDS = ()
+
+    def _make(self, capacity, shapes):
+        self._q = _RecordFIFO(self._FIELDS, capacity, shapes)
+        self.sess = None
+
+    def get_size(self):
+        return self._q.size()
+
+    def set_session(self, sess):
+        self.sess = sess
+
+
+class ApexFIFOQueue(_QueueBase):
+    """buffer_queue.py:205-272: records of one local-buffer sample (``trajectory`` transitions)."""
+    _FIELDS = ('state', 'next_state', 'previous_action', 'action', 'reward', 'done')
+
+    def __init__(self, trajectory, input_shape, output_size, queue_size, batch_size, num_actors):
+        self.trajectory, self.input_shape = trajectory, list(input_shape)
+        self.output_size, self.batch_size = output_size, batch_size
+        t = trajectory
+        self._make(queue_size, dict(state=(t, *input_shape), next_state=(t, *input_shape), previous_action=(t,),
+                                    action=(t,), reward=(t,), done=(t,)))
+
+    def append_to_queue(self, task, unrolled_state, unrolled_next_state, unrolled_previous_action, unrolled_action,
+                        unrolled_reward, unrolled_done, timeout=None):
+        self._q.put(dict(state=unrolled_state, next_state=unrolled_next_state, previous_action=unrolled_previous_action,
+                         action=unrolled_action, reward=unrolled_reward, done=unrolled_done), timeout)
+
+    def sample_batch(self, batch_size, timeout=None):
+        return self._q.get_many(batch_size, timeout)
+
+
+class R2D2FIFOQueue(_QueueBase):
+    """buffer_queue.py:69-160: records of one stored-state sequence."""
+    _FIELDS = ('state', 'previous_action', 'action', 'reward', 'done', 'previous_h', 'previous_c')
+
+    def __init__(self, seq_len, input_shape, output_size, queue_size, batch_size, num_actors, lstm_size):
+        self.seq_len, self.input_shape, self.output_size = seq_len, list(input_shape), output_size
+        self.batch_size, self.num_actors, self.lstm_size = batch_size, num_actors, lstm_size
+        s = seq_len
+        self._make(queue_size, dict(state=(s, *input_shape), previous_action=(s,), action=(s,), reward=(s,), done=(s,),
+                                    previous_h=(s, lstm_size), previous_c=(s, lstm_size)))
+
+    def append_to_queue(self, task, unrolled_state, unrolled_previous_action, unrolled_action, unrolled_reward,
+                        unrolled_done, unrolled_previous_h, unrolled_previous_c, timeout=None):
+        self._q.put(dict(state=unrolled_state, previous_action=unrolled_previous_action, action=unrolled_action,
+                         reward=unrolled_reward, done=unrolled_done, previous_h=unrolled_previous_h,
+                         previous_c=unrolled_previous_c), timeout)
+
+    def sample_batch(self, timeout=None):
+        return self._q.get_many(self.batch_size, timeout)
+
+
+class A3CFIFOQueue(_QueueBase):
+    """buffer_queue.py:7-67: capacity-1 queue of one unroll; ``sample_batch`` returns length-1 lists."""
+    _FIELDS = ('state', 'next_state', 'previous_action', 'action', 'reward', 'done')
+
+    def __init__(self, trajectory_size, input_shape, output_size, num_actors):
+        self.input_shape, self.output_size, self.num_actors = list(input_shape), output_size, num_actors
+        t = trajectory_size
+        self._make(1, dict(state=(t, *input_shape), next_state=(t, *input_shape), previous_action=(t,), action=(t,),
+                           reward=(t,), done=(t,)))
+
+    def append_to_queue(self, task, unrolled_state, unrolled_next_state, unrolled_previous_action, unrolled_action,
+                        unrolled_reward, unrolled_done, timeout=None):
+        self._q.put(dict(state=unrolled_state, next_state=unrolled_next_state, previous_action=unrolled_previous_action,
+                         action=unrolled_action, reward=unrolled_reward, done=unrolled_done), timeout)
+
+    def sample_batch(self, timeout=None):
+        return self._q.get_many(1, timeout)
+
+
+class _FieldDeques:
+    """Actor-side rolling buffers: one bounded deque per field, all appended together."""
+    _FIELDS = ()
+
+    def _reset(self, maxlen):
+        self._maxlen = int(maxlen)
+        for f in self._FIELDS:
+            setattr(self, f, collections.deque(maxlen=self._maxlen))
+
+    def _push(self, values):
+        for f, v in zip(self._FIELDS, values):
+            getattr(self, f).append(v)
+
+    def __len__(self):
+        return len(getattr(self, self._FIELDS[0]))
+
+
+class LocalBuffer(_FieldDeques):
+    """buffer_queue.py:274-318: the Ape-X actor's local transition buffer; ``sample`` draws without replacement."""
+    _FIELDS = ('state', 'next_state', 'previous_action', 'action', 'reward', 'done')
+
+    def __init__(self, capacity):
+        self._reset(capacity)
+
+    def append(self, state, next_state, previous_action, action, reward, done):
+        self._push((state, next_state, previous_action, action, reward, done))
+
+    def sample(self, batch_size):
+        order = np.random.permutation(len(self))[:batch_size]
+        return {f: [getattr(self, f)[i] for i in order] for f in self._FIELDS}
+
+
+class R2D2TrajectoryBuffer(_FieldDeques):
+    """buffer_queue.py:162-203: the last ``seq_len`` steps of an R2D2 actor."""
+    _FIELDS = ('state', 'previous_action', 'action', 'reward', 'done', 'initial_h', 'initial_c')
+
+    def __init__(self, seq_len):
+        self.seq_len = seq_len
+        self._reset(seq_len)
+
+    def append(self, state, previous_action, action, reward, done, initial_h, initial_c):
+        self._push((state, previous_action, action, reward, done, initial_h, initial_c))
+
+    def init(self):
+        self._reset(self.seq_len)
+
+    def extract(self):
+        return {f: getattr(self, f) for f in self._FIELDS}

@@ -279,3 +279,56 @@ def test_unrolled_trajectory_feeds_the_ring(native):
     assert np.array_equal(b.state[1], np.stack(sent[1]['state'])) and b.reward[0].tolist() == [0.0, 1.0, 2.0, 3.0]
     assert b.done[:, -1].all() and b.previous_c.min() == 1.0
     q.close()
+
+
+def test_record_queues_and_actor_buffers(native):
+    """In-process stand-ins of ApexFIFOQueue / R2D2FIFOQueue / A3CFIFOQueue (bounded, blocking, FIFO, static shapes) and
+    of the actor-side LocalBuffer / R2D2TrajectoryBuffer (distributed_queue/buffer_queue.py:7-318)."""
+    from distributed_reinforcement_learning_b200.distributed_queue import buffer_queue as bq
+    T, shape = 3, [84, 84, 4]
+    q = bq.ApexFIFOQueue(trajectory=T, input_shape=shape, output_size=4, queue_size=2, batch_size=32, num_actors=1)
+    q.set_session(object())
+    rec = lambda v: dict(unrolled_state=np.full((T, *shape), v, np.uint8), unrolled_next_state=np.zeros((T, *shape), np.uint8),
+                         unrolled_previous_action=np.zeros(T, np.int32), unrolled_action=np.full(T, v, np.int32),
+                         unrolled_reward=np.zeros(T, np.float32), unrolled_done=np.zeros(T, bool))
+    q.append_to_queue(task=0, **rec(1))
+    q.append_to_queue(task=0, **rec(2))
+    assert q.get_size() == 2
+    with pytest.raises(native.TimeoutError_):
+        q.append_to_queue(task=0, timeout=0.05, **rec(3))                 # full -> blocks (tf.FIFOQueue)
+    with pytest.raises(ValueError):
+        q.append_to_queue(task=0, **dict(rec(3), unrolled_reward=np.zeros(T + 1, np.float32)))   # static placeholder shapes
+    got = []
+    th = threading.Thread(target=lambda: got.append(q.sample_batch(3)))   # waits for the third record
+    th.start()
+    q.append_to_queue(task=0, timeout=2.0, **rec(3))
+    th.join(5)
+    b = got[0]
+    assert b._fields == ('state', 'next_state', 'previous_action', 'action', 'reward', 'done')
+    assert [int(a[0]) for a in b.action] == [1, 2, 3] and q.get_size() == 0   # FIFO order
+    r = bq.R2D2FIFOQueue(seq_len=T, input_shape=[84, 84, 1], output_size=4, queue_size=4, batch_size=2, num_actors=1, lstm_size=64)
+    for v in (5, 6):
+        r.append_to_queue(0, np.zeros((T, 84, 84, 1), np.uint8), np.zeros(T, np.int32), np.full(T, v, np.int32),
+                          np.zeros(T, np.float32), np.zeros(T, bool), np.zeros((T, 64), np.float32), np.zeros((T, 64), np.float32))
+    rb = r.sample_batch()
+    assert rb._fields[-2:] == ('previous_h', 'previous_c') and [int(a[0]) for a in rb.action] == [5, 6]
+    a = bq.A3CFIFOQueue(trajectory_size=T, input_shape=shape, output_size=4, num_actors=1)
+    a.append_to_queue(0, *[rec(7)[k] for k in ("unrolled_state", "unrolled_next_state", "unrolled_previous_action",
+                                              "unrolled_action", "unrolled_reward", "unrolled_done")])
+    ab = a.sample_batch()
+    assert len(ab.state) == 1 and ab.state[0].shape == (T, 84, 84, 4) and a.get_size() == 0
+    with pytest.raises(native.TimeoutError_):
+        a.sample_batch(timeout=0.05)                                      # empty -> blocks
+    lb = bq.LocalBuffer(capacity=5)
+    for i in range(8):
+        lb.append(i, i + 1, 0, 1, float(i), False)
+    assert len(lb) == 5 and list(lb.state) == [3, 4, 5, 6, 7]
+    s = lb.sample(3)
+    assert len(s["state"]) == 3 and len(set(s["state"])) == 3 and all(ns == st + 1 for st, ns in zip(s["state"], s["next_state"]))
+    tb = bq.R2D2TrajectoryBuffer(seq_len=4)
+    for i in range(6):
+        tb.append(i, 0, 1, 0.0, False, np.zeros(64), np.ones(64))
+    ex = tb.extract()
+    assert list(ex["state"]) == [2, 3, 4, 5] and set(ex) == {'state', 'previous_action', 'action', 'reward', 'done', 'initial_h', 'initial_c'}
+    tb.init()
+    assert len(tb) == 0
