@@ -32,6 +32,33 @@ def copy_src_to_dst(from_scope, to_scope):
     return run
 
 
+class _Accumulator:
+    """Per-actor accumulator of one unroll: ``initialize()`` empties it, ``append(...)`` adds one step."""
+    _FIELDS = ()
+
+    def __init__(self):
+        self.trajectory_data = collections.namedtuple('trajectory_data', list(self._FIELDS))
+
+    def initialize(self):
+        self.unroll_data = self.trajectory_data(*[[] for _ in self._FIELDS])
+
+    def _add(self, values):
+        for field, value in zip(self.unroll_data, values):
+            field.append(value)
+
+
+class UnrolledA3CTrajectory(_Accumulator):
+    """utils.py:47-78: the A3C actor's unroll; ``extract()`` stacks every field (train_a3c.py feeds it to A3CFIFOQueue)."""
+    _FIELDS = ('state', 'next_state', 'reward', 'done', 'action', 'previous_action')
+
+    def append(self, state, next_state, previous_action, action, reward, done):
+        self._add((state, next_state, reward, done, action, previous_action))
+
+    def extract(self):
+        import numpy as np
+        return {k: np.stack(v) for k, v in self.unroll_data._asdict().items()}
+
+
 class UnrolledTrajectory:
     """utils.py:80-119: per-actor accumulator of one unroll; ``extract()`` returns the nine per-step lists that
     ``FIFOQueue.append_to_queue`` takes (train_impala.py:178-189)."""

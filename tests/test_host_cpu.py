@@ -332,3 +332,17 @@ def test_record_queues_and_actor_buffers(native):
     assert list(ex["state"]) == [2, 3, 4, 5] and set(ex) == {'state', 'previous_action', 'action', 'reward', 'done', 'initial_h', 'initial_c'}
     tb.init()
     assert len(tb) == 0
+
+
+def test_unrolled_a3c_trajectory(native):
+    from distributed_reinforcement_learning_b200 import utils
+    t = utils.UnrolledA3CTrajectory()
+    t.initialize()
+    for i in range(3):
+        t.append(state=np.full((2, 2), i), next_state=np.full((2, 2), i + 1), previous_action=i, action=i + 1, reward=0.5 * i,
+                 done=(i == 2))
+    d = t.extract()
+    assert set(d) == {'state', 'next_state', 'previous_action', 'action', 'reward', 'done'}
+    assert d['state'].shape == (3, 2, 2) and d['action'].tolist() == [1, 2, 3] and d['done'].tolist() == [False, False, True]
+    t.initialize()
+    assert len(t.unroll_data.state) == 0
