@@ -8,6 +8,10 @@ This package is a CPU restatement of the reference algorithm
                                of ``model/impala_actor_critic.py``, ``agent/impala.py:31-100,132-148``
                                with TensorFlow 1.14 kernel semantics.
   * ``oracle.synthetic``    -- the seeded synthetic trajectories/parameters of SURVEY.md section 8(d).
+  * ``oracle.vtrace_c``     -- plain-C (gcc) restatement of ``optimizer/vtrace.py`` (``oracle/c/vtrace_c.c``), a second
+                               independent implementation that pins ``vtrace_np``
+  * ``oracle.apex_torch``, ``oracle.per_np`` -- the Ape-X learner step and the prioritized replay memory
+  * ``oracle.r2d2_torch``, ``oracle.a3c_torch`` -- the R2D2 and the A3C learner steps
 
 PARITY UNPINNED: the reference's arithmetic lives in tensorflow==1.14.0 (README.md:14,
 Dockerfile:2), which is not installable in this image (no wheel for CPython 3.12, no network),

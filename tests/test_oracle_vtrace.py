@@ -4,6 +4,7 @@ hypothesis property tests.  PARITY UNPINNED against TensorFlow (not installable)
 import os
 
 import numpy as np
+import pytest
 import torch
 from hypothesis import given, settings
 from hypothesis import strategies as st
@@ -137,3 +138,32 @@ def test_golden_vtrace_fixture():
     vs, rho = vt.from_importance_weights(z["log_rhos"], z["discounts"], z["rewards"], z["values"], z["bootstrap_value"])
     np.testing.assert_allclose(vs, z["vs"], rtol=1e-12)
     np.testing.assert_allclose(rho, z["clipped_rhos"], rtol=1e-12)
+
+
+def test_c_restatement_agrees_with_numpy_oracle():
+    """oracle/c/vtrace_c.c (plain C, gcc) against oracle/vtrace_np.py and the O(T^2) closed form: two independent
+    restatements of optimizer/vtrace.py pinning each other."""
+    from oracle import vtrace_c
+    rng = np.random.default_rng(5)
+    for T, B, A in ((1, 1, 2), (18, 5, 18), (32, 3, 7)):
+        lr = rng.standard_normal((T, B)) * 0.8
+        g = (rng.random((T, B)) > 0.15) * 0.99
+        r, v, boot = rng.standard_normal((T, B)), rng.standard_normal((T, B)), rng.standard_normal(B)
+        for clip in (1.0, 0.7, None):
+            vs_c, rho_c = vtrace_c.from_importance_weights(lr, g, r, v, boot, clip)
+            vs_n, rho_n = vt.from_importance_weights(lr, g, r, v, boot, clip)
+            assert np.allclose(vs_c, vs_n, rtol=1e-13, atol=1e-13) and np.allclose(rho_c, rho_n, rtol=1e-15)
+        vs_d, _ = vt.from_importance_weights_direct(lr, g, r, v, boot, 1.0)
+        assert np.allclose(vtrace_c.from_importance_weights(lr, g, r, v, boot, 1.0)[0], vs_d, rtol=1e-10, atol=1e-12)
+        logits = rng.standard_normal((2, B, T, A))
+        sm = np.exp(logits) / np.exp(logits).sum(-1, keepdims=True)
+        act = rng.integers(0, A, (B, T)).astype(np.int32)
+        args = (sm[0], sm[1], act, g.T.copy(), r.T.copy(), v.T.copy(), rng.standard_normal((B, T)), A)
+        vs_c, rho_c = vtrace_c.from_softmax(*args)
+        vs_n, rho_n = vt.from_softmax(*args)
+        assert np.allclose(vs_c, vs_n, rtol=1e-12, atol=1e-13) and np.allclose(rho_c, rho_n, rtol=1e-13)
+        adv = rng.standard_normal((B, T))
+        pg, bl, en = vtrace_c.losses(sm[1], act, adv, vs_n, v.T.copy())
+        assert pg == pytest.approx(float(vt.compute_policy_gradient_loss(sm[1], act, adv, A)), rel=1e-12)
+        assert bl == pytest.approx(float(vt.compute_baseline_loss(vs_n, v.T)), rel=1e-12)
+        assert en == pytest.approx(float(vt.compute_entropy_loss(sm[1])), rel=1e-12)
