@@ -19,8 +19,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 A, L, C = 4, 64, 1
-B, S, BI = 16, 80, 40
-METRIC = "R2D2 learner frames/sec (B=16,seq_len=80,burn_in=40,84x84x1,LSTM 64)"
+# BASELINE.json names seq_len 80 / burn_in 40; DRL_R2D2_SEQ / DRL_R2D2_BURN select another shape (the reference ships 15 / 7)
+B, S, BI = 16, int(os.environ.get("DRL_R2D2_SEQ", "80")), int(os.environ.get("DRL_R2D2_BURN", "40"))
+METRIC = "R2D2 learner frames/sec (B=16,seq_len=%d,burn_in=%d,84x84x1,LSTM 64)" % (S, BI)
 
 
 def kernel_flops(name, M):
@@ -146,8 +147,8 @@ def run(args, bench):
     line = {"metric": METRIC, "value": M / (dev_ms / K * 1e-3), "unit": "frames/s", "n_gpus": 1, "steps": K, "warmup": W,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "R2D2 learner step (BASELINE configs[4]): B=16 sequences x seq_len 80 (burn_in 40), "
-                                   "84x84x1 uint8, A=4, LSTM 64, stored-state unroll of main and target scope, BPTT, TF1 Adam",
+            "config": {"workload": "R2D2 learner step (BASELINE configs[4]): B=16 sequences x seq_len %d (burn_in %d), "
+                                   "84x84x1 uint8, A=4, LSTM 64, stored-state unroll of main and target scope, BPTT, TF1 Adam" % (S, BI),
                        "global_batch": B, "seq_len": S, "burn_in": BI, "cuda_graph": bool(use_graph),
                        "math_mode": bench.MATH_MODES[mode],
                        "l2": "activations + workspace ~0.9 GB/step > 126 MB L2; two staged slots alternate",
