@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(256) a3c_loss_kernel(A3cArgs a) {
       a.dlogits[(size_t)b * 32 + k] = pk * (dpk - sdot);
     }
     a.dv[(size_t)b * 32] = a.baseline_coef * (-2.0f * adv) * inv_n;
-    s_pi += adv * p[act];
+    s_pi += (act >= 0 && act < a.A) ? adv * p[act] : 0.f;      // tf.one_hot: an out-of-range action selects nothing
     s_bl += adv * adv;
     s_en += ent;
   }

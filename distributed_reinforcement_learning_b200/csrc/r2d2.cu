@@ -372,7 +372,8 @@ __global__ void __launch_bounds__(256) r2d2_td_kernel(R2TdArgs a) {
         const float v = a.mq[mn * a.A + k];
         if (v > best) { best = v; arg = k; }
       }
-      const float sav = a.mq[m * a.A + act];
+      const bool act_ok = act >= 0 && act < a.A;            // tf.one_hot: an out-of-range action selects nothing
+      const float sav = act_ok ? a.mq[m * a.A + act] : 0.f;
       const float nsav = a.tq[mn * a.A + arg];
       const double disc = a.done[(size_t)b * a.S + t] ? 0.0 : (double)a.discount;
       const float target = (float)r2_h(r2_hinv((double)nsav) * disc + (double)a.reward[(size_t)b * a.S + t]);
@@ -383,8 +384,10 @@ __global__ void __launch_bounds__(256) r2d2_td_kernel(R2TdArgs a) {
       ssq += diff * diff;
       if (a.dq) {
         const float g = -2.0f * w * diff / ((float)Nt * (float)a.B);
-        a.dq[m * 32 + act] = g;
-        a.dmean[m * 32] = -g;
+        if (act_ok) {
+          a.dq[m * 32 + act] = g;
+          a.dmean[m * 32] = -g;
+        }
       }
     }
     sdiff = warp_sum(sdiff);
