@@ -346,3 +346,32 @@ def test_unrolled_a3c_trajectory(native):
     assert d['state'].shape == (3, 2, 2) and d['action'].tolist() == [1, 2, 3] and d['done'].tolist() == [False, False, True]
     t.initialize()
     assert len(t.unroll_data.state) == 0
+
+
+def test_ctypes_structs_match_the_c_header(native, tmp_path):
+    """ABI drift guard: sizeof / offsetof of every struct of include/drl_b200.h as gcc lays them out must equal the
+    ctypes mirror in _native.py (a mismatch would silently scramble a configuration)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    N = native
+    pairs = [("drl_learner_config", N.LearnerConfig), ("drl_step_out", N.StepOut), ("drl_ring_batch", N.RingBatch),
+             ("drl_apex_config", N.ApexConfig), ("drl_apex_out", N.ApexOut), ("drl_a3c_config", N.A3cConfig),
+             ("drl_a3c_out", N.A3cOut), ("drl_r2d2_config", N.R2d2Config), ("drl_r2d2_out", N.R2d2Out)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "drl_b200.h"', 'int main(void) {']
+    for cname, ct in pairs:
+        lines.append('  printf("%s size %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in ct._fields_:
+            lines.append('  printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['  return 0;', '}']
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.run(["gcc", "-std=c99", "-I", inc, str(src), "-o", str(exe)], check=True, capture_output=True)
+    got = dict(ln.rsplit(" ", 1) for ln in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, ct in pairs:
+        assert int(got["%s size" % cname]) == C.sizeof(ct), cname
+        for fname, _ in ct._fields_:
+            assert int(got["%s.%s" % (cname, fname)]) == getattr(ct, fname).offset, (cname, fname)
