@@ -375,3 +375,21 @@ def test_ctypes_structs_match_the_c_header(native, tmp_path):
         assert int(got["%s size" % cname]) == C.sizeof(ct), cname
         for fname, _ in ct._fields_:
             assert int(got["%s.%s" % (cname, fname)]) == getattr(ct, fname).offset, (cname, fname)
+
+
+def test_docs_name_only_real_entry_points(native):
+    """Every drl_* name that DESIGN.md / INTEGRATION.md / README.md mention is exported by the library (wildcards like
+    drl_ring_* and family placeholders excluded)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exported = set(native.EXPORTS)
+    prefixes = {e.rsplit("_", 1)[0] for e in exported} | {"drl_learner", "drl_apex", "drl_r2d2", "drl_a3c", "drl_per",
+                                                          "drl_ring", "drl_vtrace"}
+    for doc in ("DESIGN.md", "INTEGRATION.md", "README.md"):
+        text = open(os.path.join(root, doc)).read()
+        for name in set(re.findall(r"\bdrl_[a-z0-9_]+\b", text)):
+            if name in exported or name in ("drl_b200",) or name.rstrip("_") in prefixes or name.endswith("_"):
+                continue
+            if name in ("drl_learner_config", "drl_step_out", "drl_apex_config", "drl_apex_out", "drl_a3c_config",
+                        "drl_a3c_out", "drl_r2d2_config", "drl_r2d2_out", "drl_ring_batch", "drl_learner_peer"):
+                continue
+            assert any(e.startswith(name) for e in exported), "%s mentions %s, which the library does not export" % (doc, name)
