@@ -241,3 +241,44 @@ def test_native_per_random_op_sequences(native):
             assert mem.tree.total() == ref.tree.total()
         mem.tree.close()
     run()
+
+
+def test_conv2d_restatement_against_naive_loops():
+    """tf.layers.conv2d(padding='VALID', NHWC input, HWIO kernel) = cross-correlation + bias, restated through
+    F.conv2d in oracle/impala_torch.py::_conv2d_tf; pinned here by explicit loops."""
+    from oracle import impala_torch as it
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((2, 9, 8, 3))
+    w = rng.standard_normal((4, 3, 3, 5))
+    b = rng.standard_normal(5)
+    for stride in (1, 2):
+        got = it._conv2d_tf(torch.from_numpy(x), torch.from_numpy(w), torch.from_numpy(b), stride).numpy()
+        OH, OW = (9 - 4) // stride + 1, (8 - 3) // stride + 1
+        ref = np.zeros((2, OH, OW, 5))
+        for n in range(2):
+            for oy in range(OH):
+                for ox in range(OW):
+                    patch = x[n, oy * stride:oy * stride + 4, ox * stride:ox * stride + 3, :]
+                    ref[n, oy, ox] = np.tensordot(patch, w, axes=([0, 1, 2], [0, 1, 2])) + b
+        assert got.shape == ref.shape and np.allclose(got, ref, rtol=1e-12, atol=1e-12)
+
+
+def test_tf1_adam_restatement_tracks_torch_adam_when_epsilon_is_negligible():
+    """TF1 ApplyAdam (lr_t = lr sqrt(1 - b2^t) / (1 - b1^t); w -= lr_t m / (sqrt(v) + eps)) and torch.optim.Adam
+    (bias-corrected m, v; eps outside the corrected sqrt) are the same update up to where eps enters: with gradients far
+    above eps the oracle's update must follow torch's over several steps."""
+    rng = np.random.default_rng(1)
+    w0 = rng.standard_normal(50)
+    grads = [np.sign(rng.standard_normal(50)) * (1.0 + 3.0 * np.abs(rng.standard_normal(50))) for _ in range(5)]   # |g| >= 1
+    wt = torch.tensor(w0, dtype=torch.float64, requires_grad=True)
+    opt = torch.optim.Adam([wt], lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
+    w, m, v, b1p, b2p = w0.copy(), np.zeros(50), np.zeros(50), 0.9, 0.999
+    for g in grads:
+        wt.grad = torch.tensor(g, dtype=torch.float64)
+        opt.step()
+        m += (g - m) * (1 - 0.9)
+        v += (g * g - v) * (1 - 0.999)
+        w -= m * (1e-3 * np.sqrt(1 - b2p) / (1 - b1p)) / (np.sqrt(v) + 1e-8)
+        b1p *= 0.9
+        b2p *= 0.999
+    assert np.allclose(w, wt.detach().numpy(), rtol=0, atol=1e-3 * 1e-6)      # eps placement: <= lr * 3e-7 / |g|

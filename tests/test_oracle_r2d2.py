@@ -127,3 +127,34 @@ def test_r2d2_agent_surface_and_no_cpu_fallback(native):
             ag.train(list(b["state"]), list(b["previous_action"]), list(b["action"]), list(b["h"]), list(b["c"]),
                      list(b["reward"]), list(b["done"]), b["weight"])
         assert "no CPU fallback" in str(ei.value)
+
+
+def test_lstm_cell_restatement_agrees_with_torch_lstmcell():
+    """The TF 1.14 LSTMCell restatement (kernel [x|h] -> gates i, j, f, o; forget_bias 1.0 outside the bias variable)
+    against an independent implementation: torch.nn.LSTMCell (gates i, f, g, o) with the weights permuted and the
+    forget bias folded in.  Pins the cell used by oracle/impala_torch.py::lstm and oracle/r2d2_torch.py::network."""
+    from oracle import impala_torch as it
+    torch.manual_seed(0)
+    n, X, L = 5, 37, 16
+    W = torch.randn(X + L, 4 * L, dtype=torch.float64) * 0.3
+    bias = torch.randn(4 * L, dtype=torch.float64) * 0.1
+    x, h0, c0 = (torch.randn(n, X, dtype=torch.float64), torch.randn(n, L, dtype=torch.float64) * 0.5,
+                 torch.randn(n, L, dtype=torch.float64))
+    h1, c1, _ = it.lstm({"lstm.w": W, "lstm.b": bias}, x, h0, c0)
+    cell = torch.nn.LSTMCell(X, L).double()
+    i, j, f, o = torch.chunk(W, 4, dim=1)                      # TF column blocks
+    bi, bj, bf, bo = torch.chunk(bias, 4)
+    with torch.no_grad():
+        Wt = torch.cat([i, f, j, o], dim=1)                    # torch row blocks: i, f, g, o
+        cell.weight_ih.copy_(Wt[:X].t())
+        cell.weight_hh.copy_(Wt[X:].t())
+        cell.bias_ih.copy_(torch.cat([bi, bf + 1.0, bj, bo]))  # forget_bias = 1.0
+        cell.bias_hh.zero_()
+        h_ref, c_ref = cell(x, (h0, c0))
+    assert torch.allclose(h1, h_ref, rtol=1e-12, atol=1e-13) and torch.allclose(c1, c_ref, rtol=1e-12, atol=1e-13)
+    # and the R2D2 network step uses the same cell
+    p = rt.init_params(0, torch.float64)
+    b = rt.make_sequences(2, S=2, seed=1)
+    q, h2, c2, _ = rt.network(p, torch.from_numpy(b["state"][:, 0]).double() / 255, torch.from_numpy(b["previous_action"][:, 0]).long(),
+                              torch.from_numpy(b["h"][:, 0]).double(), torch.from_numpy(b["c"][:, 0]).double(), 4)
+    assert h2.shape == (2, 64) and torch.all(h2.abs() < 1) and q.shape == (2, 4)
