@@ -1,12 +1,16 @@
-"""Generates the committed golden vectors for the IMPALA learner step (and the Ape-X / R2D2 / A3C steps) from the
-float64 oracles.
+"""Generates the committed golden vectors of the IMPALA learner step, of optimizer/vtrace.py and of the Ape-X / R2D2
+steps by EXECUTING THE UNMODIFIED REFERENCE FILES (``/root/reference/agent/impala.py`` etc.) over the TF 1.14 API
+stand-in ``oracle/tf1_shim`` in float64 (``oracle/ref_exec.py``); the A3C vectors (out of scope) still come from its
+float64 restatement.
 
     python tests/golden/make_golden.py [impala] [vtrace] [apex] [r2d2] [a3c]     # default: all; writes tests/golden/*.npz
 
-PARITY UNPINNED: the reference (TF 1.14) cannot be imported in this image, so these vectors pin the
-ORACLE (oracle/impala_torch.py, float64) -- not TensorFlow -- against regressions, and give the GPU tests
-a fixture that does not depend on re-running the oracle.  Inputs are regenerated from the stored seed by
-oracle/synthetic.py::make_batch and oracle/impala_torch.py::init_params(0).
+Needs the reference checkout (build container only).  Every file records ``source``.  What these vectors pin: the
+restatements under ``oracle/`` (CPU suite, float64, ~1e-12) and the CUDA path (``-m gpu`` suite, 1e-4) against the
+reference's own graph-construction code; TensorFlow's op kernels themselves are restated by the shim (see its
+docstring) -- ``tests/golden/make_golden_tf1.py`` regenerates the same files under a real tensorflow==1.14.0 where
+one exists.  Inputs are regenerated from the stored seed by oracle/synthetic.py::make_batch and
+oracle/impala_torch.py::init_params(0).
 """
 import os
 import sys
@@ -24,23 +28,33 @@ from oracle import synthetic, vtrace_np  # noqa: E402
 STRIDE = 61
 
 
+SOURCE = "reference files executed over oracle/tf1_shim (float64)"
+
+
 def learner_case(B, T, A, seed, path):
+    """agent/impala.py:132-148 ``Agent.train`` executed once; taps/gradients fetched from the agent's own graph."""
+    from oracle import ref_exec
     batch = synthetic.make_batch(B, T=T, A=A, seed=seed)
     params = it.init_params(0, torch.float32, num_action=A)
-    L = it.Learner(params, torch.float64, "reference", trajectory=T, num_action=A)
-    (pi, bl, en, lr), out, g, gn = L.train(*[batch[k] for k in synthetic.TRAIN_FIELDS], return_all=True)
+    args = [batch[k] for k in synthetic.TRAIN_FIELDS]
+    R = ref_exec.ReferenceImpala(params, trajectory=T, num_action=A)
+    f = R.fetch(args, ["vs", "clipped_rho", "vs_plus_1", "pg_advantage", "unrolled_first_policy",
+                       "unrolled_first_value", "total_loss"])
+    g = {n: torch.from_numpy(np.asarray(v)) for n, v in R.gradients(args).items()}
+    gn = float(np.sqrt(sum(float(torch.sum(v.double() ** 2)) for v in g.values())))
+    pi, bl, en, lr = R.train(*args)
     rec = dict(B=B, T=T, A=A, seed=seed, pi_loss=pi, baseline_loss=bl, entropy=en, learning_rate=lr, grad_norm=gn,
-               total_loss=float(out["total_loss"]))
-    for k in ("vs", "clipped_rho", "vs_plus_1", "pg_advantage", "first_policy", "first_value"):
-        rec[k] = out[k].detach().numpy()
-    for n, v in g.items():
-        v = v.detach().numpy()
-        # big tensors (LSTM kernel: 3.7M floats): strided sample + l2 norm; full tensors for the rest
-        if v.size > 70000:
-            rec["gradsample_" + n] = v.ravel()[::STRIDE].astype(np.float32)
-            rec["gradl2_" + n] = np.float64(np.sqrt(np.sum(v.astype(np.float64) ** 2)))
-        else:
-            rec["grad_" + n] = v.astype(np.float32)
+               total_loss=float(f["total_loss"]), source=SOURCE)
+    for k, src in (("vs", "vs"), ("clipped_rho", "clipped_rho"), ("vs_plus_1", "vs_plus_1"),
+                   ("pg_advantage", "pg_advantage"), ("first_policy", "unrolled_first_policy"),
+                   ("first_value", "unrolled_first_value")):
+        rec[k] = f[src]
+    _pack_grads(rec, g)
+    # the applied update (clip_by_global_norm 40 + TF1 RMSProp, one step): strided samples of the new parameters / slots
+    for n, v in R.params().items():
+        rec["paramsample_" + n] = v.ravel()[::STRIDE]
+    for n, v in R.rms().items():
+        rec["rmssample_" + n] = v.ravel()[::STRIDE]
     np.savez_compressed(path, **rec)
     return rec
 
@@ -51,13 +65,17 @@ def vtrace_case(path):
     kw = dict(log_rhos=rng.standard_normal((T, B)) * 0.7, discounts=(rng.random((T, B)) > 0.1) * 0.99,
               rewards=rng.standard_normal((T, B)), values=rng.standard_normal((T, B)),
               bootstrap_value=rng.standard_normal(B))
-    vs, rho = vtrace_np.from_importance_weights(**kw)
-    np.savez_compressed(path, vs=vs, clipped_rhos=rho, **kw)
+    from oracle import ref_exec
+    ref = ref_exec.load(("optimizer.vtrace",), float_dtype=torch.float64)
+    tf, vt = ref.tf, ref["optimizer.vtrace"]
+    vs, rho = tf.Session().run(list(vt.from_importance_weights(**{k: tf.constant(np.asarray(v, np.float64))
+                                                                   for k, v in kw.items()})))
+    np.savez_compressed(path, vs=vs, clipped_rhos=rho, source=SOURCE, **kw)
 
 
 def _pack_grads(rec, g):
     for n, v in g.items():
-        v = v.detach().numpy()
+        v = v.detach().numpy() if hasattr(v, "detach") else np.asarray(v)
         if v.size > 70000:
             rec["gradsample_" + n] = v.ravel()[::STRIDE].astype(np.float32)
             rec["gradl2_" + n] = np.float64(np.sqrt(np.sum(v.astype(np.float64) ** 2)))
@@ -66,28 +84,44 @@ def _pack_grads(rec, g):
 
 
 def apex_case(path, B=3, A=4, seed=1357):
-    """oracle/apex_torch.py: one distributed_train step (inputs regenerated from make_transitions(B, A, seed),
+    """agent/apex.py:135-154 ``distributed_train`` executed once (inputs regenerated from make_transitions(B, A, seed),
     parameters from init_params(0) / init_params(1))."""
     from oracle import apex_torch as ax
+    from oracle import ref_exec
     b = ax.make_transitions(B, A=A, seed=seed)
-    L = ax.Learner(dtype=torch.float64, num_action=A)
-    (loss, td), out, g, gn, lr = L.distributed_train(*[b[k] for k in ax.TRAIN_FIELDS], return_all=True)
-    rec = dict(B=B, A=A, seed=seed, loss=loss, td_error=td, grad_norm=gn, learning_rate=lr)
-    for k in ("main_q", "next_main_q", "target_q", "target_value", "state_action_value"):
-        rec[k] = out[k].detach().numpy()
+    p, tp = ax.init_params(0, torch.float32, num_action=A), ax.init_params(1, torch.float32, num_action=A)
+    R = ref_exec.ReferenceApex(p, tp, num_action=A)
+    args = [b[k] for k in ax.TRAIN_FIELDS]
+    f = R.fetch(args, ["main_q_value", "next_main_q_value", "target_q_value", "target_value", "state_action_value",
+                       "learning_rate"])
+    g = {n: torch.from_numpy(np.asarray(v)) for n, v in R.gradients(R.feed(*args)).items()}
+    gn = float(np.sqrt(sum(float(torch.sum(v.double() ** 2)) for v in g.values())))
+    loss, td = R.agent.distributed_train(*args)
+    rec = dict(B=B, A=A, seed=seed, loss=loss, td_error=td, grad_norm=gn, learning_rate=float(f["learning_rate"]),
+               source=SOURCE)
+    for k, src in (("main_q", "main_q_value"), ("next_main_q", "next_main_q_value"), ("target_q", "target_q_value"),
+                   ("target_value", "target_value"), ("state_action_value", "state_action_value")):
+        rec[k] = f[src]
     _pack_grads(rec, g)
     np.savez_compressed(path, **rec)
     return rec
 
 
 def r2d2_case(path, B=2, S=6, bi=2, seed=2468):
+    """agent/r2d2.py:132-159 ``Agent.train`` executed once."""
     from oracle import r2d2_torch as rt
+    from oracle import ref_exec
     b = rt.make_sequences(B, S=S, seed=seed)
-    L = rt.Learner(dtype=torch.float64, seq_len=S, burn_in=bi)
-    (loss, td), out, g, gn = L.train(*[b[k] for k in rt.TRAIN_FIELDS], return_all=True)
-    rec = dict(B=B, S=S, burn_in=bi, seed=seed, loss=loss, td_error=td, grad_norm=gn)
+    p, tp = rt.init_params(0, torch.float32), rt.init_params(1, torch.float32)
+    R = ref_exec.ReferenceR2D2(p, tp, seq_len=S, burn_in=bi)
+    args = [b[k] for k in rt.TRAIN_FIELDS]
+    f = R.fetch(args, ["main_q", "target_q", "target_value", "state_action_value"])
+    g = {n: torch.from_numpy(np.asarray(v)) for n, v in R.gradients(R.feed(*args)).items()}
+    gn = float(np.sqrt(sum(float(torch.sum(v.double() ** 2)) for v in g.values())))
+    loss, td = R.agent.train(*args)
+    rec = dict(B=B, S=S, burn_in=bi, seed=seed, loss=loss, td_error=td, grad_norm=gn, source=SOURCE)
     for k in ("main_q", "target_q", "target_value", "state_action_value"):
-        rec[k] = out[k].detach().numpy()
+        rec[k] = f[k]
     _pack_grads(rec, g)
     np.savez_compressed(path, **rec)
     return rec
@@ -98,7 +132,8 @@ def a3c_case(path, B=3, A=4, seed=97531):
     b = at.make_transitions(B, A=A, seed=seed)
     L = at.Learner(dtype=torch.float64, num_action=A)
     (pi, bl, en, lr), out, g, gn = L.train(*[b[k] for k in at.TRAIN_FIELDS], return_all=True)
-    rec = dict(B=B, A=A, seed=seed, pi_loss=pi, baseline_loss=bl, entropy=en, learning_rate=lr, grad_norm=gn)
+    rec = dict(B=B, A=A, seed=seed, pi_loss=pi, baseline_loss=bl, entropy=en, learning_rate=lr, grad_norm=gn,
+               source="oracle/a3c_torch.py (float64 restatement; A3C is out of scope, not executed from the reference)")
     for k in ("policy", "value", "next_value", "advantage"):
         rec[k] = out[k].detach().numpy()
     _pack_grads(rec, g)
@@ -109,8 +144,10 @@ def a3c_case(path, B=3, A=4, seed=97531):
 if __name__ == "__main__":
     which = set(sys.argv[1:]) or {"impala", "vtrace", "apex", "r2d2", "a3c"}
     if "impala" in which:
-        r = learner_case(2, 6, 18, 4321, os.path.join(HERE, "impala_step_B2_T6.npz"))
-        print("pi %.6f bl %.6f ent %.6f gn %.6f" % (r["pi_loss"], r["baseline_loss"], r["entropy"], r["grad_norm"]))
+        for B, T, seed in ((2, 6, 4321), (4, 20, 1234)):        # small case; BASELINE configs[0] (T=20, B=4)
+            r = learner_case(B, T, 18, seed, os.path.join(HERE, "impala_step_B%d_T%d.npz" % (B, T)))
+            print("B%d T%d: pi %.6f bl %.6f ent %.6f gn %.6f" % (B, T, r["pi_loss"], r["baseline_loss"], r["entropy"],
+                                                                 r["grad_norm"]))
     if "vtrace" in which:
         vtrace_case(os.path.join(HERE, "vtrace_T18_B8.npz"))
     if "apex" in which:

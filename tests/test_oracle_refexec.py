@@ -1,0 +1,347 @@
+"""PIN of the oracle to the reference itself: the UNMODIFIED reference files (``/root/reference/agent/impala.py``,
+``optimizer/vtrace.py``, ``model/impala_actor_critic.py``, ``distributed_queue/buffer_queue.py``, ``utils.py``; and the
+Ape-X / R2D2 files) are imported and executed here over ``oracle/tf1_shim`` (a TF 1.14 API stand-in on torch-CPU that
+restates only TF's op semantics -- see its docstring) and must agree with the restatements under ``oracle/`` on every
+slice, window, loss, stop_gradient and optimizer decision: V-trace taps, the three losses, all 24 gradients, three
+RMSProp steps with slots and global_step, both reward-clipping modes, the reference-shaped 54-copy graph against the
+deduplicated forward, variable names/order/sharing, parameter_sync, single-step inference and the FIFO queue's order.
+
+CPU-only; needs the reference checkout (present in the build container, absent on the GPU box -> skipped there;
+the committed goldens in tests/golden/ are generated from these executed-reference runs by make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import impala_torch as it
+from oracle import ref_exec, synthetic, vtrace_np
+
+pytestmark = pytest.mark.skipif(not ref_exec.available(), reason="reference checkout not present")
+
+F64 = dict(rtol=0, atol=0)
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)) if b.size else 0.0
+
+
+def _case(B, T, A, seed=4321, **cfg):
+    batch = synthetic.make_batch(B, T=T, A=A, seed=seed)
+    params = it.init_params(0, torch.float32, num_action=A)
+    return batch, params, [batch[k] for k in synthetic.TRAIN_FIELDS], dict(trajectory=T, num_action=A, **cfg)
+
+
+TAPS = ("vs", "clipped_rho", "vs_plus_1", "pg_advantage", "pi_loss", "baseline_loss", "entropy", "total_loss")
+
+
+@pytest.mark.parametrize("clipping", ["abs_one", "soft_asymmetric"])
+def test_impala_executed_reference_equals_restatement(clipping):
+    """agent/impala.py:31-100,132-148 executed == oracle/impala_torch.py (reference-shaped AND deduplicated)."""
+    batch, params, args, cfg = _case(2, 6, 18, reward_clipping=clipping)
+    R = ref_exec.ReferenceImpala(params, **cfg)
+    f = R.fetch(args, TAPS + ("unrolled_first_policy", "unrolled_first_value", "unrolled_middle_value",
+                              "unrolled_last_value", "discounts", "clipped_r_ph"))
+    rg = R.gradients(args)
+    for shaped, tol in (("reference", 1e-13), ("dedup", 1e-11)):
+        L = it.Learner(params, torch.float64, shaped, **cfg)
+        out, g = L.gradients(*args)
+        for k in TAPS:
+            assert _rel(out[k].detach().numpy(), f[k]) <= tol, (shaped, k)
+        assert _rel(out["first_policy"].detach().numpy(), f["unrolled_first_policy"]) <= tol
+        assert _rel(out["middle_value"].detach().numpy(), f["unrolled_middle_value"]) <= tol
+        assert _rel(out["last_value"].detach().numpy(), f["unrolled_last_value"]) <= tol
+        assert set(g) == set(rg) and len(rg) == 24
+        for n in g:
+            assert _rel(g[n].numpy(), rg[n]) <= tol * 10, (shaped, n)
+    assert f["clipped_r_ph"].min() >= (-1.0 if clipping == "abs_one" else -1.5)
+
+
+def test_impala_three_train_steps_track_the_executed_reference():
+    """Agent.train x3: returned scalars, every parameter, the RMSProp ``rms`` slots (ms0 = 1, eps inside the sqrt),
+    global_step and the learning rate -- TF1 optimizer semantics as restated in the shim's docstring."""
+    batch, params, args, cfg = _case(2, 6, 18)
+    R = ref_exec.ReferenceImpala(params, **cfg)
+    L = it.Learner(params, torch.float64, "dedup", **cfg)
+    for step in range(3):
+        r, o = R.train(*args), L.train(*args)
+        for a, b in zip(r[:3], o[:3]):
+            assert abs(a - b) <= 1e-9 * max(abs(b), 1.0)
+        assert abs(r[3] - o[3]) < 1e-10                  # lr: float32 polynomial_decay in the oracle, exact here
+        assert R.global_step() == step + 1 == L.step
+        for n, v in R.params().items():
+            assert _rel(v, L.params[n].detach().numpy()) < 1e-9, n
+        for n, v in R.rms().items():
+            assert _rel(v, L.ms[n].numpy()) < 1e-9, n
+    assert all(np.any(v != 1.0) and np.all(v > 0.9) for v in R.rms().values())    # slots started at ones (TF1), not zeros
+
+
+def test_baseline_config0_b4_t20_54_graph_copies_equal_one_forward():
+    """BASELINE configs[0] (T=20, B=4): the reference's 3 x 18 per-timestep network copies (executed) against the
+    ONE forward over the 20 distinct rows that the CUDA path runs (shift identity)."""
+    batch, params, args, cfg = _case(4, 20, 18, seed=1234)
+    R = ref_exec.ReferenceImpala(params, **cfg)
+    f = R.fetch(args, TAPS)
+    rg = R.gradients(args)
+    L = it.Learner(params, torch.float64, "dedup", **cfg)
+    out, g = L.gradients(*args)
+    for k in TAPS:
+        assert _rel(out[k].detach().numpy(), f[k]) <= 1e-11, k
+    for n in g:
+        assert _rel(g[n].numpy(), rg[n]) <= 1e-10, n
+
+
+def test_float32_execution_is_within_the_parity_bar_of_float64():
+    """The same reference graph evaluated in float32 (TF's arithmetic type) sits inside the 1e-4 bar that the CUDA path
+    is held to: the bar is meaningful for a float32 implementation of this graph."""
+    batch, params, args, cfg = _case(2, 6, 18)
+    f64 = ref_exec.ReferenceImpala(params, **cfg).fetch(args, TAPS)
+    R32 = ref_exec.ReferenceImpala(params, float_dtype=torch.float32, **cfg)
+    f32 = R32.fetch(args, TAPS)
+    assert f32["vs"].dtype == np.float32
+    for k in TAPS:
+        assert _rel(f32[k], f64[k]) < 1e-4, k
+    R32.ref.tf._shim.FLOAT = torch.float64
+
+
+def test_variable_names_sharing_and_parameter_sync():
+    """model/impala_actor_critic.py:47-109 re-enters variable_scope('impala', reuse=AUTO_REUSE) 55 times: exactly 24
+    trainable variables result, named as TF1 names them; a second agent (train_impala.py:64-80, 'actor_0') adds its own
+    24 and utils.copy_src_to_dst (parameter_sync) copies learner -> actor in creation order."""
+    ref = ref_exec.load(float_dtype=torch.float64)
+    tf = ref.tf
+    kw = dict(trajectory=5, input_shape=[84, 84, 4], num_action=6, lstm_hidden_size=256, discount_factor=0.99,
+              start_learning_rate=6e-4, end_learning_rate=0.0, learning_frame=10 ** 9, baseline_loss_coef=1.0,
+              entropy_coef=0.05, gradient_clip_norm=40.0, reward_clipping="abs_one")
+    learner = ref["agent.impala"].Agent(model_name="learner", learner_name="learner", **kw)
+    names = [v.op_name for v in tf.trainable_variables()]
+    assert len(names) == 24
+    assert names[:2] == ["learner/impala/conv2d/kernel", "learner/impala/conv2d/bias"]
+    assert names[10:12] == ["learner/impala/rnn/lstm_cell/kernel", "learner/impala/rnn/lstm_cell/bias"]
+    assert names[-2:] == ["learner/impala/dense_7/kernel", "learner/impala/dense_7/bias"]
+    assert tuple(tf.get_default_graph().var_by_name["learner/impala/rnn/lstm_cell/kernel"]._shape) == (3648, 1024)
+    actor = ref["agent.impala"].Agent(model_name="actor_0", learner_name="learner", **kw)
+    assert len(tf.trainable_variables()) == 48 and len(actor.global_to_session) == 24
+    sess = tf.Session()
+    learner.set_session(sess)
+    src = tf.trainable_variables("learner")
+    dst = tf.trainable_variables("actor_0")
+    assert any(np.any(s.numpy() != d.numpy()) for s, d in zip(src, dst))
+    actor.sess = sess
+    actor.parameter_sync()
+    assert all(np.array_equal(s.numpy(), d.numpy()) for s, d in zip(src, dst))
+    # single-step inference (agent/impala.py:118-130) on the synced actor == the oracle's ``network``
+    rng = np.random.default_rng(3)
+    state = rng.integers(0, 256, (84, 84, 4), dtype=np.uint8)
+    h, c = rng.standard_normal(256).astype(np.float32) * 0.3, rng.standard_normal(256).astype(np.float32)
+    np.random.seed(0)
+    action, policy, mx, h1, c1 = actor.get_policy_and_action(state, 2, h, c)
+    p = {n: torch.from_numpy(v.numpy()) for n, v in zip([s for s, _ in it.param_specs(num_action=6)], dst)}
+    x = torch.from_numpy((state[None].astype(np.float64) / 255).astype(np.float32)).double()
+    pol, val, oc, oh = it.network(p, x, torch.tensor([2]), torch.from_numpy(h[None]).double(),
+                                  torch.from_numpy(c[None]).double(), 6, 256)
+    assert _rel(policy, pol[0].numpy()) < 1e-12 and mx == max(policy) and 0 <= action < 6
+    assert _rel(h1, oh[0].numpy()) < 1e-12 and _rel(c1, oc[0].numpy()) < 1e-12      # returns (.., h, c) in that order
+
+
+def test_static_placeholder_shapes_reject_a_wrong_trajectory_length():
+    """Error behaviour at the boundary: feeding T+1 steps to the [None, T, ...] placeholders raises."""
+    batch, params, args, cfg = _case(2, 6, 18)
+    R = ref_exec.ReferenceImpala(params, **cfg)
+    bad = synthetic.make_batch(2, T=7, A=18, seed=1)
+    with pytest.raises(ValueError):
+        R.train(*[bad[k] for k in synthetic.TRAIN_FIELDS])
+
+
+# ---- optimizer/vtrace.py, function by function -------------------------------------------------------------------
+def _run(ref, tensors, feeds=None):
+    return ref.tf.Session().run(tensors, feed_dict=feeds)
+
+
+def test_vtrace_functions_executed_equal_numpy_and_c_restatements():
+    ref = ref_exec.load(("optimizer.vtrace",), float_dtype=torch.float64)
+    vt, tf = ref["optimizer.vtrace"], ref.tf
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "vtrace_T18_B8.npz"))
+    kw = {k: z[k] for k in ("log_rhos", "discounts", "rewards", "values", "bootstrap_value")}
+    vs, rho = _run(ref, list(vt.from_importance_weights(**{k: tf.constant(v) for k, v in kw.items()})))
+    np.testing.assert_allclose(vs, z["vs"], rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(rho, z["clipped_rhos"], rtol=1e-13, atol=1e-13)
+    ovs, orho = vtrace_np.from_importance_weights(**kw)
+    np.testing.assert_allclose(vs, ovs, rtol=1e-13, atol=1e-13)
+    from oracle import vtrace_c
+    cvs, crho = vtrace_c.from_importance_weights(**kw)               # plain-C restatement (gcc, built on demand)
+    np.testing.assert_allclose(vs, cvs, rtol=1e-12, atol=1e-12)
+    # clip_rho_threshold honoured, clip_pg_rho_threshold dead, cs hard-coded at 1 (optimizer/vtrace.py:72-80)
+    a = _run(ref, list(vt.from_importance_weights(clip_rho_threshold=0.5, clip_pg_rho_threshold=7.0,
+                                                  **{k: tf.constant(v) for k, v in kw.items()})))
+    b = vtrace_np.from_importance_weights(clip_rho_threshold=0.5, **kw)
+    np.testing.assert_allclose(a[0], b[0], rtol=1e-13, atol=1e-13)
+    assert a[1].max() <= 0.5
+
+    rng = np.random.default_rng(11)
+    B, T, A = 5, 9, 7
+    sm = lambda x: np.exp(x) / np.exp(x).sum(-1, keepdims=True)
+    mu, pi = sm(rng.standard_normal((B, T, A))), sm(rng.standard_normal((B, T, A)))
+    act = rng.integers(0, A, (B, T)).astype(np.int32)
+    disc = (rng.random((B, T)) > 0.1) * 0.99
+    rew, val, nval = rng.standard_normal((B, T)), rng.standard_normal((B, T)), rng.standard_normal((B, T))
+    c = tf.constant
+    got = _run(ref, list(vt.from_softmax(c(mu), c(pi), c(act), c(disc), c(rew), c(val), c(nval), A)))
+    exp = vtrace_np.from_softmax(mu, pi, act, disc, rew, val, nval, A)
+    np.testing.assert_allclose(got[0], exp[0], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(got[1], exp[1], rtol=1e-12, atol=1e-12)
+    adv = rng.standard_normal((B, T))
+    got = _run(ref, [vt.compute_policy_gradient_loss(c(pi), c(act), c(adv), A), vt.compute_baseline_loss(c(val), c(nval)),
+                     vt.compute_entropy_loss(c(pi)), vt.log_probs_from_softmax_and_actions(c(pi), c(act), A)] +
+               list(vt.split_data(c(val))))
+    assert got[0] == pytest.approx(vtrace_np.compute_policy_gradient_loss(pi, act, adv, A), rel=1e-12)
+    assert got[1] == pytest.approx(vtrace_np.compute_baseline_loss(val, nval), rel=1e-12)
+    assert got[2] == pytest.approx(vtrace_np.compute_entropy_loss(pi), rel=1e-12)
+    np.testing.assert_allclose(got[3], vtrace_np.log_probs_from_softmax_and_actions(pi, act, A), rtol=1e-12)
+    for g, e in zip(got[4:], vtrace_np.split_data(val)):
+        np.testing.assert_array_equal(g, e)
+
+
+# ---- distributed_queue/buffer_queue.py:418-512 against the pinned-ring replacement ---------------------------------
+def test_reference_fifo_queue_order_equals_the_ring(native_or_none=None):
+    ref = ref_exec.load(("distributed_queue.buffer_queue",), float_dtype=torch.float64)
+    tf = ref.tf
+    T, shape, A, L, cap, batch = 5, [6, 6, 2], 4, 8, 8, 3
+    rq = ref["distributed_queue.buffer_queue"].FIFOQueue(T, shape, A, cap, batch, 2, L)
+    rq.set_session(tf.Session())
+    try:
+        from distributed_reinforcement_learning_b200.distributed_queue import buffer_queue
+        ours = buffer_queue.FIFOQueue(T, shape, A, cap, batch, 2, L, pinned=False)
+    except Exception:                                   # library not built: the reference-side half still runs
+        ours = None
+    rng = np.random.default_rng(5)
+
+    def rec():
+        return dict(unrolled_state=rng.integers(0, 256, (T, *shape), dtype=np.uint8),
+                    unrolled_next_state=rng.integers(0, 256, (T, *shape), dtype=np.uint8),
+                    unrolled_reward=rng.standard_normal(T).astype(np.float32), unrolled_done=rng.random(T) < 0.3,
+                    unrolled_behavior_policy=rng.random((T, A)).astype(np.float32),
+                    unrolled_action=rng.integers(0, A, T).astype(np.int32),
+                    unrolled_previous_action=rng.integers(0, A, T).astype(np.int32),
+                    unrolled_previous_h=rng.standard_normal((T, L)).astype(np.float32),
+                    unrolled_previous_c=rng.standard_normal((T, L)).astype(np.float32))
+
+    recs = [rec() for _ in range(7)]
+    for i, r in enumerate(recs):
+        rq.append_to_queue(task=i % 2, **r)
+        if ours is not None:
+            ours.append_to_queue(task=i % 2, **r)
+    assert rq.get_size() == 7 and (ours is None or ours.get_size() == 7)
+    for lo in (0, 3):
+        rb = rq.sample_batch()
+        assert rb._fields == ("state", "next_state", "reward", "done", "behavior_policy", "action", "previous_action",
+                              "previous_h", "previous_c")
+        for i in range(batch):
+            np.testing.assert_array_equal(rb.state[i], recs[lo + i]["unrolled_state"])
+            np.testing.assert_array_equal(rb.previous_c[i], recs[lo + i]["unrolled_previous_c"])
+        if ours is not None:
+            ob = ours.sample_batch()
+            for name in ("state", "reward", "done", "behavior_policy", "action", "previous_action", "previous_h",
+                         "previous_c"):
+                np.testing.assert_array_equal(np.stack(getattr(ob, name)), np.stack(getattr(rb, name)), err_msg=name)
+    assert rq.get_size() == 1
+
+
+def test_learner_loop_call_pattern_on_the_executed_reference():
+    """train_impala.py:93-113 replayed with the reference's own FIFOQueue and Agent (over the shim): gate on
+    size > 3*batch, sample_batch, np.stack of every field, Agent.train; scalars equal the oracle fed the same stacks."""
+    B, T, A, L = 2, 5, 6, 256
+    ref = ref_exec.load(float_dtype=torch.float64)
+    tf = ref.tf
+    params = it.init_params(0, torch.float32, num_action=A)
+    R = ref_exec.ReferenceImpala(params, trajectory=T, num_action=A)          # fresh graph with the learner agent
+    tf = R.ref.tf
+    queue = R.ref["distributed_queue.buffer_queue"].FIFOQueue(T, [84, 84, 4], A, 128, B, 1, L)
+    queue.set_session(R.sess)
+    O = it.Learner(params, torch.float64, "dedup", trajectory=T, num_action=A)
+    big = synthetic.make_batch(3 * B + 1 + B, T=T, A=A, seed=77)
+    for i in range(big["state"].shape[0]):
+        queue.append_to_queue(task=0, unrolled_state=big["state"][i], unrolled_next_state=big["state"][i],
+                              unrolled_reward=big["reward"][i], unrolled_done=big["done"][i],
+                              unrolled_behavior_policy=big["behavior_policy"][i], unrolled_action=big["action"][i],
+                              unrolled_previous_action=big["previous_action"][i],
+                              unrolled_previous_h=big["initial_h"][i], unrolled_previous_c=big["initial_c"][i])
+    steps = 0
+    while queue.get_size() > 3 * B:
+        batch = queue.sample_batch()
+        kw = dict(state=np.stack(batch.state), reward=np.stack(batch.reward), action=np.stack(batch.action),
+                  done=np.stack(batch.done), behavior_policy=np.stack(batch.behavior_policy),
+                  previous_action=np.stack(batch.previous_action), initial_h=np.stack(batch.previous_h),
+                  initial_c=np.stack(batch.previous_c))
+        got = R.agent.train(**kw)
+        exp = O.train(**kw)
+        for a, b in zip(got[:3], exp[:3]):
+            assert abs(a - b) <= 1e-9 * max(abs(b), 1.0)
+        steps += 1
+    assert steps == 2 and queue.get_size() == 3 * B - 1
+
+
+# ---- next rows: Ape-X and R2D2 agents executed -------------------------------------------------------------------
+def test_apex_executed_reference_equals_restatement():
+    from oracle import apex_torch as ax
+    A = 4
+    b = ax.make_transitions(3, A=A, seed=1357)
+    p, tp = ax.init_params(0, torch.float32, num_action=A), ax.init_params(1, torch.float32, num_action=A)
+    R = ref_exec.ReferenceApex(p, tp, num_action=A)
+    L = ax.Learner(p, tp, torch.float64, num_action=A)
+    args = [b[k] for k in ax.TRAIN_FIELDS]
+    out, g = L.gradients(*args[:6], is_weight=args[6])
+    f = R.fetch(args, ["main_q_value", "next_main_q_value", "target_q_value", "target_value", "state_action_value",
+                       "value_loss", "next_action"])
+    for k, ok in (("main_q_value", "main_q"), ("next_main_q_value", "next_main_q"), ("target_q_value", "target_q"),
+                  ("target_value", "target_value"), ("state_action_value", "state_action_value"),
+                  ("value_loss", "value_loss")):
+        assert _rel(out[ok].detach().numpy(), f[k]) < 1e-12, k
+    assert np.array_equal(f["next_action"], out["next_action"].numpy())
+    rg = R.gradients(R.feed(*args))
+    assert len(rg) == 22                                  # target variables receive no gradient (None in TF)
+    for n in g:
+        assert _rel(g[n].numpy(), rg[n]) < 1e-11, n
+    td_single = R.agent.get_td_error(*args[:6])
+    assert _rel(td_single, L.get_td_error(*args[:6])) < 1e-12
+    for _ in range(3):
+        r1, r2 = R.agent.distributed_train(*args), L.distributed_train(*args)
+        assert r1[0] == pytest.approx(r2[0], rel=1e-6) and _rel(r1[1], r2[1]) < 1e-6
+    for n, v in R.params().items():
+        assert _rel(v, L.params[n].detach().numpy()) < 1e-6, n
+    m, v = R.adam_slots()
+    assert max(_rel(m[n], L.m[n].numpy()) for n in m) < 1e-5 and max(_rel(v[n], L.v[n].numpy()) for n in v) < 1e-5
+    assert any(np.any(R.target_params()[n] != R.params()[n]) for n in R.var)
+    R.agent.target_to_main()                              # despite the name: target <- main (utils.py:27-32)
+    L.target_to_main()
+    for n in R.var:
+        assert np.array_equal(R.target_params()[n], R.params()[n])
+        assert _rel(R.target_params()[n], L.target[n].numpy()) < 1e-6
+
+
+def test_r2d2_executed_reference_equals_restatement():
+    from oracle import r2d2_torch as rt
+    S, bi = 6, 2
+    b = rt.make_sequences(2, S=S, seed=2468)
+    p, tp = rt.init_params(0, torch.float32), rt.init_params(1, torch.float32)
+    R = ref_exec.ReferenceR2D2(p, tp, seq_len=S, burn_in=bi)
+    L = rt.Learner(p, tp, torch.float64, seq_len=S, burn_in=bi)
+    args = [b[k] for k in rt.TRAIN_FIELDS]
+    out, g = L.gradients(*args[:7], weight=args[7])
+    f = R.fetch(args, ["main_q", "target_q", "target_value", "state_action_value", "value_loss"])
+    for k in ("main_q", "target_q", "target_value", "state_action_value", "value_loss"):
+        assert _rel(out[k].detach().numpy(), f[k]) < 1e-12, k
+    rg = R.gradients(R.feed(*args))
+    assert len(rg) == 18
+    for n in g:
+        assert _rel(g[n].numpy(), rg[n]) < 1e-11, n
+    for _ in range(3):
+        r1, r2 = R.agent.train(*args), L.train(*args)
+        assert r1[0] == pytest.approx(r2[0], rel=1e-6) and _rel(r1[1], r2[1]) < 1e-5
+    for n, v in R.params().items():
+        assert _rel(v, L.params[n].detach().numpy()) < 1e-6, n
+    R.agent.main_to_target()
+    L.main_to_target()
+    for n in R.var:
+        assert np.array_equal(R.target_params()[n], R.params()[n])
