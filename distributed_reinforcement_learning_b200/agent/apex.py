@@ -12,6 +12,7 @@ values -- so the learner branch of ``train_apex.py:82-155`` runs on it unchanged
   Agent.train                 agent/apex.py:156-168
 """
 import os
+import threading
 
 import numpy as np
 
@@ -46,6 +47,7 @@ class Agent:
         self._engine = None
         self._slot = 0
         self._last = {}
+        self._lock = threading.RLock()   # actor threads sync from / act on this agent while the learner thread trains
         _AGENTS[model_name] = self
 
     # ---- engine management -----------------------------------------------------------
@@ -93,19 +95,26 @@ class Agent:
         else:
             self._target = self._main.copy()
 
+    def _snapshot_params(self):
+        with self._lock:
+            self._ensure_init()
+            if self._engine is not None:
+                return self._engine.get_params(MAIN), self._engine.get_params(TARGET)
+            return self._main.copy(), self._target.copy()
+
     def parameter_sync(self):
         """agent/apex.py:81-82 (utils.copy_src_to_dst(learner_name, model_name)): both scopes are trainable
         variables of the learner, so both are copied."""
         src = _AGENTS.get(self.learner_name)
         if src is None or src is self:
             return
-        src._ensure_init()
-        src._pull_state()
-        self._ensure_init()
-        self._main, self._target = src._main.copy(), src._target.copy()
-        if self._engine is not None:
-            self._engine.set_params(self._main, MAIN)
-            self._engine.set_params(self._target, TARGET)
+        main, target = src._snapshot_params()            # trainable variables only, into caller-owned buffers
+        with self._lock:
+            self._ensure_init()
+            self._main, self._target = main, target
+            if self._engine is not None:
+                self._engine.set_params(self._main, MAIN)
+                self._engine.set_params(self._target, TARGET)
 
     def set_session(self, sess):
         self.sess = sess
@@ -156,7 +165,9 @@ class Agent:
     def get_td_error(self, state, next_state, previous_action, action, reward, done):
         """agent/apex.py:116-133 -> |target_value - state_action_value| [n]."""
         st = self._u8(np.stack(state))
-        eng = self._get_engine(st.shape[0])
+        # evaluation only: reuse the training engine and go through it in chunks of its batch size; never rebuild it
+        # for a larger n (train_apex.py calls this with `trajectory` transitions, which may exceed batch_size)
+        eng = self._engine if self._engine is not None else self._get_engine(st.shape[0])
         out = np.empty(st.shape[0], np.float32)
         B = eng.B
         ns = self._u8(np.stack(next_state))
@@ -192,3 +203,17 @@ class Agent:
     grad_norm = property(lambda self: self._last.get("grad_norm"))
     value_loss = property(lambda self: self._last.get("loss"))
     num_env_frames = property(lambda self: self._last.get("step", (self._opt or {}).get("step", 0)))
+
+
+def _locked(fn):
+    def wrapper(self, *a, **k):
+        with self._lock:
+            return fn(self, *a, **k)
+    wrapper.__name__, wrapper.__doc__ = fn.__name__, fn.__doc__
+    return wrapper
+
+
+# actor threads call these on a shared agent while the learner thread trains (in-process launch mode)
+for _n in ('save_weights', 'load_weights', 'set_session', 'target_to_main', 'get_policy_and_action', 'get_td_error', '_train'):
+    if hasattr(Agent, _n):
+        setattr(Agent, _n, _locked(getattr(Agent, _n)))

@@ -18,6 +18,7 @@ initialised, every rank feeds its own shard of the global batch to ``train`` and
 bucket is all-reduced (SUM) over NCCL before the identical replicated update.
 """
 import os
+import threading
 
 import numpy as np
 
@@ -50,7 +51,11 @@ class Agent:
         self.model_name = model_name
         self.learner_name = learner_name
         self.device = int(os.environ.get("LOCAL_RANK", "0"))
-        self.use_cuda_graph = os.environ.get("DRL_B200_CUDA_GRAPH", "0") == "1"
+        # the whole step is one CUDA graph by default (the benchmarked path); DRL_B200_CUDA_GRAPH=0 launches eagerly
+        self.use_cuda_graph = os.environ.get("DRL_B200_CUDA_GRAPH", "1") != "0"
+        # actor threads call parameter_sync()/get_policy_and_action() while the learner thread trains (in-process mode
+        # of train_impala.py): every method that touches the agent's state or its engine holds this lock
+        self._lock = threading.RLock()
         self.sess = None
         self._kw = dict(num_action=num_action, lstm_hidden_size=lstm_hidden_size, input_shape=tuple(input_shape))
         self._params = None            # flat float32 (host copy, authoritative while no engine exists)
@@ -94,75 +99,87 @@ class Agent:
     # ---- reference API ---------------------------------------------------------------
     def save_weights(self, path):
         """tf.train.Saver().save: parameters + RMSProp slots + global_step, TF layouts, one .npz."""
-        self._ensure_init()
-        self._pull_state()
-        if not path.endswith(".npz"):
-            path = path + ".npz"
-        np.savez(path, params=self._params, ms=self._ms, step=np.int64(self._step))
+        with self._lock:
+            self._ensure_init()
+            self._pull_state()
+            if not path.endswith(".npz"):
+                path = path + ".npz"
+            np.savez(path, params=self._params, ms=self._ms, step=np.int64(self._step))
 
     def load_weights(self, path):
-        if not path.endswith(".npz"):
-            path = path + ".npz"
-        z = np.load(path)
-        n = impala_actor_critic.param_count(**self._kw)
-        if z["params"].size != n:
-            raise ValueError("checkpoint has %d parameters, this agent has %d" % (z["params"].size, n))
-        self._params = z["params"].astype(np.float32)
-        self._ms = z["ms"].astype(np.float32)
-        self._step = int(z["step"])
-        if self._engine is not None:
-            self._engine.set_params(self._params)
-            self._engine.set_opt_state(self._ms, self._step)
+        with self._lock:
+            if not path.endswith(".npz"):
+                path = path + ".npz"
+            z = np.load(path)
+            n = impala_actor_critic.param_count(**self._kw)
+            if z["params"].size != n:
+                raise ValueError("checkpoint has %d parameters, this agent has %d" % (z["params"].size, n))
+            self._params = z["params"].astype(np.float32)
+            self._ms = z["ms"].astype(np.float32)
+            self._step = int(z["step"])
+            if self._engine is not None:
+                self._engine.set_params(self._params)
+                self._engine.set_opt_state(self._ms, self._step)
+
+    def _snapshot_params(self):
+        """Parameters only, into a buffer the CALLER owns (no rebinding of this agent's fields from a foreign thread)."""
+        with self._lock:
+            self._ensure_init()
+            return self._engine.get_params() if self._engine is not None else self._params.copy()
 
     def parameter_sync(self):
-        """Copy the learner's variables into this agent (utils.copy_src_to_dst, utils.py:6-22)."""
+        """Copy the learner's variables into this agent (utils.copy_src_to_dst, utils.py:6-22): trainable variables
+        only -- the RMSProp slots are not part of the copy."""
         src = _AGENTS.get(self.learner_name)
         if src is None or src is self:
             return
-        src._ensure_init()
-        src._pull_state()
-        self._params = src._params.copy()
-        if self._ms is None:
-            self._ms = np.ones_like(self._params)
-        if self._engine is not None:
-            self._engine.set_params(self._params)
+        params = src._snapshot_params()
+        with self._lock:
+            self._params = params
+            if self._ms is None:
+                self._ms = np.ones_like(self._params)
+            if self._engine is not None:
+                self._engine.set_params(self._params)
 
     def set_session(self, sess):
         """Stores the session object (unused) and (re-)initialises every variable, as
         ``sess.run(tf.global_variables_initializer())`` does (agent/impala.py:114-116)."""
-        self.sess = sess
-        self._params = None
-        self._ensure_init()
-        if self._engine is not None:
-            self._engine.set_params(self._params)
-            self._engine.set_opt_state(self._ms, self._step)
+        with self._lock:
+            self.sess = sess
+            self._params = None
+            self._ensure_init()
+            if self._engine is not None:
+                self._engine.set_params(self._params)
+                self._engine.set_opt_state(self._ms, self._step)
 
     def get_policy_and_action(self, state, previous_action, h, c):
         """agent/impala.py:118-130 -> (action, policy, max(policy), h', c')."""
-        eng = self._engine if self._engine is not None else self._get_engine(1)
-        st = np.asarray(state)
-        if st.dtype != np.uint8:
-            st = np.clip(np.rint(st), 0, 255).astype(np.uint8)
-        policy, rh, rc = eng.act(st[None], np.asarray([previous_action], np.int32),
-                                 np.asarray(h, np.float32)[None], np.asarray(c, np.float32)[None])
-        policy, rh, rc = policy[0], rh[0], rc[0]
-        p = policy.astype(np.float64)
-        action = np.random.choice(self.num_action, p=p / p.sum())
-        return action, policy, max(policy), rh, rc
+        with self._lock:
+            eng = self._engine if self._engine is not None else self._get_engine(1)
+            st = np.asarray(state)
+            if st.dtype != np.uint8:
+                st = np.clip(np.rint(st), 0, 255).astype(np.uint8)
+            policy, rh, rc = eng.act(st[None], np.asarray([previous_action], np.int32),
+                                     np.asarray(h, np.float32)[None], np.asarray(c, np.float32)[None])
+            policy, rh, rc = policy[0], rh[0], rc[0]
+            p = policy.astype(np.float64)
+            action = np.random.choice(self.num_action, p=p / p.sum())
+            return action, policy, max(policy), rh, rc
 
     def train(self, state, reward, action, done, behavior_policy, previous_action, initial_h, initial_c):
         """agent/impala.py:132-148 -> (pi_loss, value_loss, entropy, learning_rate).
         ``state`` is the raw uint8 [B, T, 84, 84, 4] batch; the /255 of :133 happens on the device."""
-        state = np.asarray(state)
-        if state.dtype != np.uint8:
-            raise TypeError("state must be uint8 frames (the /255 normalisation runs on the GPU)")
-        eng = self._get_engine(state.shape[0])
-        slot = self._slot
-        self._slot = (self._slot + 1) % eng.num_slots
-        eng.stage(slot, state, reward, action, done, behavior_policy, previous_action, initial_h, initial_c)
-        out = eng.step(slot)
-        self._last = out
-        return out["pi_loss"], out["baseline_loss"], out["entropy"], out["learning_rate"]
+        with self._lock:
+            state = np.asarray(state)
+            if state.dtype != np.uint8:
+                raise TypeError("state must be uint8 frames (the /255 normalisation runs on the GPU)")
+            eng = self._get_engine(state.shape[0])
+            slot = self._slot
+            self._slot = (self._slot + 1) % eng.num_slots
+            eng.stage(slot, state, reward, action, done, behavior_policy, previous_action, initial_h, initial_c)
+            out = eng.step(slot)
+            self._last = out
+            return out["pi_loss"], out["baseline_loss"], out["entropy"], out["learning_rate"]
 
     # ---- graph attributes as last-step values (agent/impala.py:68-96) -----------------
     def _tap(self, name):

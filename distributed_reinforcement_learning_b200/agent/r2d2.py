@@ -9,6 +9,7 @@ the learner branch of ``train_r2d2.py:87-165`` runs on it unchanged, with the TF
   Agent.main_q_value_test / target_q_value_test   agent/r2d2.py:193-217
 """
 import os
+import threading
 
 import numpy as np
 
@@ -41,6 +42,7 @@ class Agent:
         self._engine = None
         self._slot = 0
         self._last = {}
+        self._lock = threading.RLock()   # actor threads sync from / act on this agent while the learner thread trains
         _AGENTS[model_name] = self
 
     def _ensure_init(self):
@@ -103,17 +105,24 @@ class Agent:
         self._last = out
         return out["loss"], td
 
+    def _snapshot_params(self):
+        with self._lock:
+            self._ensure_init()
+            if self._engine is not None:
+                return self._engine.get_params(MAIN), self._engine.get_params(TARGET)
+            return self._main.copy(), self._target.copy()
+
     def parameter_sync(self):
         src = _AGENTS.get(self.learner_name)
         if src is None or src is self:
             return
-        src._ensure_init()
-        src._pull_state()
-        self._ensure_init()
-        self._main, self._target = src._main.copy(), src._target.copy()
-        if self._engine is not None:
-            self._engine.set_params(self._main, MAIN)
-            self._engine.set_params(self._target, TARGET)
+        main, target = src._snapshot_params()            # trainable variables only, into caller-owned buffers
+        with self._lock:
+            self._ensure_init()
+            self._main, self._target = main, target
+            if self._engine is not None:
+                self._engine.set_params(self._main, MAIN)
+                self._engine.set_params(self._target, TARGET)
 
     def main_to_target(self):
         self._ensure_init()
@@ -156,3 +165,17 @@ class Agent:
 
     value_loss = property(lambda self: self._last.get("loss"))
     grad_norm = property(lambda self: self._last.get("grad_norm"))
+
+
+def _locked(fn):
+    def wrapper(self, *a, **k):
+        with self._lock:
+            return fn(self, *a, **k)
+    wrapper.__name__, wrapper.__doc__ = fn.__name__, fn.__doc__
+    return wrapper
+
+
+# actor threads call these on a shared agent while the learner thread trains (in-process launch mode)
+for _n in ('save_weights', 'load_weights', 'set_session', 'main_to_target', 'get_action', 'get_td_error', 'train', 'main_q_value_test', 'target_q_value_test'):
+    if hasattr(Agent, _n):
+        setattr(Agent, _n, _locked(getattr(Agent, _n)))

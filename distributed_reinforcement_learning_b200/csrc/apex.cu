@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <string>
+#include <mutex>
 #include <vector>
 
 #include "layer_defs.cuh"
@@ -554,6 +555,8 @@ struct ApexSlot {
 using namespace drl;
 
 struct drl_apex {
+  std::recursive_mutex mu;   // every C-ABI entry point locks the handle (actor threads call parameter_sync -> get_params
+                             // on the learner's handle while the learner thread trains; ctypes drops the GIL)
   drl_apex_config cfg{};
   int B = 0, A = 0, mode = 2;
   ApexLayout pl{};
@@ -1003,6 +1006,7 @@ int drl_apex_destroy(drl_apex* h) {
 
 int drl_apex_param_count(const drl_apex* h, int64_t* n) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_apex*>(h)->mu);
   if (!n) { set_error("null argument"); return DRL_ERR_INVALID; }
   *n = h->pl.packed_total;
   return DRL_OK;
@@ -1010,6 +1014,7 @@ int drl_apex_param_count(const drl_apex* h, int64_t* n) {
 
 int drl_apex_set_params(drl_apex* h, int32_t which, const float* host_flat, int64_t n) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_apex*>(h)->mu);
   if (which != DRL_APEX_MAIN && which != DRL_APEX_TARGET) { set_error("which must be DRL_APEX_MAIN or DRL_APEX_TARGET"); return DRL_ERR_INVALID; }
   if (!host_flat || n != h->pl.packed_total) { set_error("set_params: expected %lld floats, got %lld", (long long)h->pl.packed_total, (long long)n); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
@@ -1019,6 +1024,7 @@ int drl_apex_set_params(drl_apex* h, int32_t which, const float* host_flat, int6
 }
 int drl_apex_get_params(drl_apex* h, int32_t which, float* host_flat, int64_t n) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_apex*>(h)->mu);
   if (which != DRL_APEX_MAIN && which != DRL_APEX_TARGET) { set_error("which must be DRL_APEX_MAIN or DRL_APEX_TARGET"); return DRL_ERR_INVALID; }
   if (!host_flat || n != h->pl.packed_total) { set_error("get_params: expected %lld floats", (long long)h->pl.packed_total); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
@@ -1028,6 +1034,7 @@ int drl_apex_get_params(drl_apex* h, int32_t which, float* host_flat, int64_t n)
 int drl_apex_set_opt_state(drl_apex* h, const float* host_m, const float* host_v, int64_t n, int64_t step,
                            float beta1_power, float beta2_power) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_apex*>(h)->mu);
   if (!host_m || !host_v || n != h->pl.packed_total) { set_error("set_opt_state: expected %lld floats", (long long)h->pl.packed_total); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
   DRL_TRY(upload_flat(h, h->adam_m, host_m));
@@ -1041,6 +1048,7 @@ int drl_apex_set_opt_state(drl_apex* h, const float* host_m, const float* host_v
 int drl_apex_get_opt_state(drl_apex* h, float* host_m, float* host_v, int64_t n, int64_t* step, float* beta1_power,
                            float* beta2_power) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_apex*>(h)->mu);
   if (n != h->pl.packed_total) { set_error("get_opt_state: expected %lld floats", (long long)h->pl.packed_total); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
   if (host_m) DRL_TRY(download_flat(h, h->adam_m, host_m));
@@ -1057,6 +1065,7 @@ int drl_apex_get_opt_state(drl_apex* h, float* host_m, float* host_v, int64_t n,
 }
 int drl_apex_get_grads(drl_apex* h, float* host_flat, int64_t n) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_apex*>(h)->mu);
   if (!host_flat || n != h->pl.packed_total) { set_error("get_grads: expected %lld floats", (long long)h->pl.packed_total); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
   return download_flat(h, h->grads, host_flat);
@@ -1064,6 +1073,7 @@ int drl_apex_get_grads(drl_apex* h, float* host_flat, int64_t n) {
 
 int drl_apex_target_to_main(drl_apex* h) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_apex*>(h)->mu);
   DRL_TRY(set_device(h));
   DRL_CUDA_CHECK(cudaMemcpyAsync(h->target, h->params, h->pl.padded_total * sizeof(float), cudaMemcpyDeviceToDevice, h->compute));
   pdl_break(h->compute);
@@ -1075,6 +1085,7 @@ int drl_apex_stage(drl_apex* h, int32_t slot, const uint8_t* state, const uint8_
                    const int32_t* previous_action, const int32_t* action, const float* reward, const uint8_t* done,
                    const float* is_weight) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_apex*>(h)->mu);
   if (slot < 0 || slot >= h->cfg.num_slots) { set_error("slot %d out of range", slot); return DRL_ERR_INVALID; }
   if (!state || !next_state || !previous_action || !action || !reward || !done) { set_error("stage: null input pointer"); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
@@ -1088,6 +1099,7 @@ int drl_apex_stage(drl_apex* h, int32_t slot, const uint8_t* state, const uint8_
 
 int drl_apex_step_async(drl_apex* h, int32_t slot) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_apex*>(h)->mu);
   if (slot < 0 || slot >= h->cfg.num_slots) { set_error("slot %d out of range", slot); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
   return run_step(h, slot);
@@ -1095,18 +1107,21 @@ int drl_apex_step_async(drl_apex* h, int32_t slot) {
 
 int drl_apex_forward_backward(drl_apex* h, int32_t slot) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_apex*>(h)->mu);
   if (slot < 0 || slot >= h->cfg.num_slots) { set_error("slot %d out of range", slot); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
   return run_forward_backward(h, slot);
 }
 int drl_apex_grad_bucket(drl_apex* h, void** dev_ptr, int64_t* count) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_apex*>(h)->mu);
   if (dev_ptr) *dev_ptr = h->grads;
   if (count) *count = h->pl.padded_total + 4;
   return DRL_OK;
 }
 int drl_apex_apply(drl_apex* h, float grad_scale) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_apex*>(h)->mu);
   if (!(grad_scale > 0.f)) { set_error("apply: grad_scale must be > 0"); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
   return run_apply(h, grad_scale);
@@ -1114,6 +1129,7 @@ int drl_apex_apply(drl_apex* h, float grad_scale) {
 
 int drl_apex_wait(drl_apex* h, drl_apex_out* out, float* td_error) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_apex*>(h)->mu);
   if (!h->pending) { set_error("wait: no step in flight"); return DRL_ERR_STATE; }
   DRL_TRY(set_device(h));
   h->pending = false;
@@ -1141,6 +1157,7 @@ int drl_apex_td_error(drl_apex* h, int32_t n, const uint8_t* state, const uint8_
                       const int32_t* previous_action, const int32_t* action, const float* reward, const uint8_t* done,
                       float* td_error) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_apex*>(h)->mu);
   if (n < 1 || n > h->B) { set_error("td_error: n must be in [1, %d]", h->B); return DRL_ERR_INVALID; }
   if (!state || !next_state || !previous_action || !action || !reward || !done || !td_error) { set_error("td_error: null pointer"); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
@@ -1173,6 +1190,7 @@ int drl_apex_td_error(drl_apex* h, int32_t n, const uint8_t* state, const uint8_
 
 int drl_apex_act(drl_apex* h, int32_t n, const uint8_t* state, const int32_t* previous_action, float* q_value) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_apex*>(h)->mu);
   if (n < 1 || n > 2 * h->B) { set_error("act: n must be in [1, %d]", 2 * h->B); return DRL_ERR_INVALID; }
   if (!state || !previous_action || !q_value) { set_error("act: null pointer"); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
@@ -1197,6 +1215,7 @@ int drl_apex_act(drl_apex* h, int32_t n, const uint8_t* state, const int32_t* pr
 int drl_apex_taps(drl_apex* h, float* main_q, float* next_main_q, float* target_q, float* target_value,
                   float* state_action_value) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_apex*>(h)->mu);
   DRL_TRY(set_device(h));
   if (h->last_n < 1) { set_error("taps: no step or td_error call has run"); return DRL_ERR_STATE; }
   DRL_CUDA_CHECK(cudaStreamSynchronize(h->compute));
@@ -1211,6 +1230,7 @@ int drl_apex_taps(drl_apex* h, float* main_q, float* next_main_q, float* target_
 
 int drl_apex_read_buffer(drl_apex* h, const char* name, float* host_dst, int64_t n) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_apex*>(h)->mu);
   if (!name || !host_dst) { set_error("null argument"); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
   if (h->last_n < 1) { set_error("read_buffer: no step or td_error call has run"); return DRL_ERR_STATE; }
@@ -1236,6 +1256,7 @@ int drl_apex_read_buffer(drl_apex* h, const char* name, float* host_dst, int64_t
 int drl_apex_profile_step(drl_apex* h, int32_t slot, char* names, int64_t names_len, float* ms, int32_t max_kernels,
                           int32_t* count) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_apex*>(h)->mu);
   if (slot < 0 || slot >= h->cfg.num_slots) { set_error("slot %d out of range", slot); return DRL_ERR_INVALID; }
   if (!names || !ms || !count) { set_error("null argument"); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
@@ -1258,6 +1279,7 @@ int drl_apex_profile_step(drl_apex* h, int32_t slot, char* names, int64_t names_
 
 int drl_apex_last_step_ms(drl_apex* h, float* ms) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_apex*>(h)->mu);
   if (!ms) { set_error("null argument"); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
   DRL_CUDA_CHECK(cudaEventSynchronize(h->ev_stop));
@@ -1267,6 +1289,7 @@ int drl_apex_last_step_ms(drl_apex* h, float* ms) {
 
 int drl_apex_stream(drl_apex* h, void** stream) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_apex*>(h)->mu);
   if (!stream) { set_error("null argument"); return DRL_ERR_INVALID; }
   *stream = h->compute;
   return DRL_OK;
@@ -1274,6 +1297,7 @@ int drl_apex_stream(drl_apex* h, void** stream) {
 
 int drl_apex_launches_per_step(const drl_apex* h, int32_t* n) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_apex*>(h)->mu);
   if (!n) { set_error("null argument"); return DRL_ERR_INVALID; }
   *n = h->launches;     // valid after the first step
   return DRL_OK;
@@ -1320,6 +1344,7 @@ int drl_a3c_stage(drl_a3c* h, int32_t slot, const uint8_t* state, const uint8_t*
 }
 int drl_a3c_step_async(drl_a3c* h, int32_t slot) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_apex*>(h)->mu);
   if (h->algo != 1) { set_error("not an A3C handle"); return DRL_ERR_INVALID; }
   return drl_apex_step_async(h, slot);
 }
@@ -1328,6 +1353,7 @@ int drl_a3c_grad_bucket(drl_a3c* h, void** dev_ptr, int64_t* count) { return drl
 int drl_a3c_apply(drl_a3c* h, float grad_scale) { return drl_apex_apply(h, grad_scale); }
 int drl_a3c_wait(drl_a3c* h, drl_a3c_out* out) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_apex*>(h)->mu);
   drl_apex_out o{};
   DRL_TRY(drl_apex_wait(h, &o, nullptr));
   if (out) {
@@ -1343,6 +1369,7 @@ int drl_a3c_step(drl_a3c* h, int32_t slot, drl_a3c_out* out) {
 }
 int drl_a3c_act(drl_a3c* h, int32_t n, const uint8_t* state, const int32_t* previous_action, float* policy, float* value) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_apex*>(h)->mu);
   if (n < 1 || n > 2 * h->B) { set_error("act: n must be in [1, %d]", 2 * h->B); return DRL_ERR_INVALID; }
   if (!state || !previous_action) { set_error("act: null pointer"); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
@@ -1361,6 +1388,7 @@ int drl_a3c_act(drl_a3c* h, int32_t n, const uint8_t* state, const int32_t* prev
 }
 int drl_a3c_taps(drl_a3c* h, float* policy, float* value, float* next_value, float* advantage) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_apex*>(h)->mu);
   DRL_TRY(set_device(h));
   if (h->last_n < 1) { set_error("taps: no step has run"); return DRL_ERR_STATE; }
   DRL_CUDA_CHECK(cudaStreamSynchronize(h->compute));

@@ -162,7 +162,8 @@ struct OptState {
   float* norm_partials; int nblk;            // partial sums of squares; grid size of the two optimizer kernels
   int npart;                                 // how many partials the update kernel sums (nblk, or world * nblk_r)
   // peer exchange (peer.cu): the update kernel first waits for the peers' barrier-1 flags (null: single replica)
-  const uint32_t* wait_flags; const uint32_t* wait_epoch; int wait_world; uint32_t* wait_err;
+  const uint32_t* wait_flags; const uint32_t* wait_epoch; int wait_world;
+  uint32_t* wait_err; uint32_t* wait_err_host; unsigned long long wait_timeout_ns;   // peer_sync.cuh::PeerErr
   int wait_parts;                            // exchange instances to wait for
   long long* step;                           // device global_step
   float* lr_cur;                             // device scalar
@@ -197,7 +198,9 @@ struct PeerTable {                 // device pointers into every rank's buffers 
   float* partials[kMaxPeers];      // [world * nblk_r] partial squared norms
   uint32_t* flags[kMaxPeers];      // [2 * kPeerParts][kMaxPeers] barrier epochs (phase = 2 * part + {ready, delivered})
   uint32_t* epoch[kMaxPeers];      // per part 4 words: epochs completed (x2), CTA ticket counter (own entry only)
-  uint32_t* err[kMaxPeers];        // barrier time-out report (only the own entry is used)
+  uint32_t* err[kMaxPeers];        // barrier time-out word in device memory (only the own entry is used)
+  uint32_t* err_host;              // its mapped pinned copy for the host
+  unsigned long long timeout_ns;   // barrier time-out (DRL_B200_PEER_TIMEOUT_S)
 };
 struct PeerPlan {
   PeerTable t;

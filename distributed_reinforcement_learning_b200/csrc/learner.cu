@@ -6,6 +6,7 @@
 
 #include <stdlib.h>
 
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -148,7 +149,15 @@ struct drl_learner {
   PeerPlan plan{};                           // peer table + the update's OptState on the reduced buffer
   std::vector<void*> peer_opened;            // bases returned by cudaIpcOpenMemHandle
   uint32_t* h_peer_err = nullptr;            // pinned copy of the barrier time-out word
+  bool failed = false;                       // a peer barrier timed out: the replica is out of step with its peers and
+                                             // refuses every further step / state read (drl_learner_wait reported it)
+  // One handle is used by one host thread at a time (include/drl_b200.h); the documented in-process mode of the
+  // reference's launchers nevertheless has actor threads call parameter_sync() -> get_params on the learner's handle
+  // while the learner thread trains, and ctypes drops the GIL.  Every entry point therefore takes this lock (the
+  // pinned staging buffer h_flat, `pending`, `last_out` and the graph caches are all guarded by it).
+  std::recursive_mutex mu;
 };
+#define DRL_LOCK(h) std::lock_guard<std::recursive_mutex> _drl_lock((h)->mu)
 
 namespace {
 
@@ -166,6 +175,14 @@ size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 int check_handle(const drl_learner* h) {
   if (!h) { set_error("null learner handle"); return DRL_ERR_INVALID; }
+  return DRL_OK;
+}
+int check_not_failed(const drl_learner* h) {
+  if (h->failed) {
+    set_error("learner handle is in the failed state (a peer-exchange barrier timed out): parameters and optimizer "
+              "state are not readable and no further step can run");
+    return DRL_ERR_STATE;
+  }
   return DRL_OK;
 }
 
@@ -463,6 +480,7 @@ int drl_learner_create(const drl_learner_config* cfg, drl_learner** out) {
     o.nblk = 148 * 4;
     o.npart = o.nblk;
     o.wait_flags = nullptr; o.wait_epoch = nullptr; o.wait_world = 0; o.wait_err = nullptr; o.wait_parts = 0;
+    o.wait_err_host = nullptr; o.wait_timeout_ns = 0;
     DRL_TRY(dev_alloc(h, &o.norm_partials, o.nblk));
     o.step = h->d_step; o.lr_cur = h->d_lr; o.out = h->d_out; o.loss_sums = v.loss_sums;
     o.start_lr = cfg->start_learning_rate; o.end_lr = cfg->end_learning_rate; o.learning_frame = cfg->learning_frame;
@@ -539,6 +557,7 @@ int drl_learner_destroy(drl_learner* h) {
 
 int drl_learner_param_count(const drl_learner* h, int64_t* n) {
   DRL_TRY(check_handle(h));
+  DRL_LOCK(const_cast<drl_learner*>(h));
   if (!n) { set_error("null argument"); return DRL_ERR_INVALID; }
   *n = h->pl.packed_total;
   return DRL_OK;
@@ -546,6 +565,7 @@ int drl_learner_param_count(const drl_learner* h, int64_t* n) {
 
 int drl_learner_set_params(drl_learner* h, const float* host_flat, int64_t n) {
   DRL_TRY(check_handle(h));
+  DRL_LOCK(const_cast<drl_learner*>(h));
   if (!host_flat || n != h->pl.packed_total) { set_error("set_params: expected %lld floats, got %lld", (long long)h->pl.packed_total, (long long)n); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
   DRL_TRY(upload_flat(h, h->params, host_flat, 0.0f));
@@ -554,12 +574,15 @@ int drl_learner_set_params(drl_learner* h, const float* host_flat, int64_t n) {
 }
 int drl_learner_get_params(drl_learner* h, float* host_flat, int64_t n) {
   DRL_TRY(check_handle(h));
+  DRL_LOCK(const_cast<drl_learner*>(h));
+  DRL_TRY(check_not_failed(h));
   if (!host_flat || n != h->pl.packed_total) { set_error("get_params: expected %lld floats", (long long)h->pl.packed_total); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
   return download_flat(h, h->params, host_flat);
 }
 int drl_learner_set_opt_state(drl_learner* h, const float* host_ms_flat, int64_t n, int64_t step) {
   DRL_TRY(check_handle(h));
+  DRL_LOCK(const_cast<drl_learner*>(h));
   if (!host_ms_flat || n != h->pl.packed_total) { set_error("set_opt_state: expected %lld floats", (long long)h->pl.packed_total); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
   DRL_TRY(upload_flat(h, h->ms, host_ms_flat, 1.0f));
@@ -569,6 +592,8 @@ int drl_learner_set_opt_state(drl_learner* h, const float* host_ms_flat, int64_t
 }
 int drl_learner_get_opt_state(drl_learner* h, float* host_ms_flat, int64_t n, int64_t* step) {
   DRL_TRY(check_handle(h));
+  DRL_LOCK(const_cast<drl_learner*>(h));
+  DRL_TRY(check_not_failed(h));
   if (n != h->pl.packed_total) { set_error("get_opt_state: expected %lld floats", (long long)h->pl.packed_total); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
   if (host_ms_flat) DRL_TRY(download_flat(h, h->ms, host_ms_flat));
@@ -582,6 +607,8 @@ int drl_learner_get_opt_state(drl_learner* h, float* host_ms_flat, int64_t n, in
 }
 int drl_learner_get_grads(drl_learner* h, float* host_flat, int64_t n) {
   DRL_TRY(check_handle(h));
+  DRL_LOCK(const_cast<drl_learner*>(h));
+  DRL_TRY(check_not_failed(h));
   if (!host_flat || n != h->pl.packed_total) { set_error("get_grads: expected %lld floats", (long long)h->pl.packed_total); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
   return download_flat(h, h->peer_on ? reinterpret_cast<float*>(h->comm) : h->bucket, host_flat);
@@ -591,6 +618,7 @@ int drl_learner_stage(drl_learner* h, int32_t slot, const uint8_t* state, const 
                       const uint8_t* done, const float* behavior_policy, const int32_t* previous_action,
                       const float* initial_h, const float* initial_c) {
   DRL_TRY(check_handle(h));
+  DRL_LOCK(const_cast<drl_learner*>(h));
   if (slot < 0 || slot >= (int)h->slots.size()) { set_error("slot %d out of range", slot); return DRL_ERR_INVALID; }
   if (!state || !reward || !action || !done || !behavior_policy || !previous_action || !initial_h || !initial_c) {
     set_error("stage: null input pointer");
@@ -619,6 +647,8 @@ int drl_learner_stage(drl_learner* h, int32_t slot, const uint8_t* state, const 
 
 int drl_learner_forward_backward(drl_learner* h, int32_t slot) {
   DRL_TRY(check_handle(h));
+  DRL_LOCK(const_cast<drl_learner*>(h));
+  DRL_TRY(check_not_failed(h));
   if (slot < 0 || slot >= (int)h->slots.size()) { set_error("slot %d out of range", slot); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
   return run_forward_backward(h, slot);
@@ -626,6 +656,7 @@ int drl_learner_forward_backward(drl_learner* h, int32_t slot) {
 
 int drl_learner_grad_bucket(drl_learner* h, void** dev_ptr, int64_t* count) {
   DRL_TRY(check_handle(h));
+  DRL_LOCK(const_cast<drl_learner*>(h));
   if (dev_ptr) *dev_ptr = h->bucket;
   if (count) *count = h->pl.padded_total + 4;
   return DRL_OK;
@@ -633,6 +664,8 @@ int drl_learner_grad_bucket(drl_learner* h, void** dev_ptr, int64_t* count) {
 
 int drl_learner_apply(drl_learner* h) {
   DRL_TRY(check_handle(h));
+  DRL_LOCK(const_cast<drl_learner*>(h));
+  DRL_TRY(check_not_failed(h));
   DRL_TRY(set_device(h));
   return run_apply(h);
 }
@@ -640,6 +673,7 @@ int drl_learner_apply(drl_learner* h) {
 // ---- gradient exchange over NVLink peer memory (peer.cu) -------------------------------------------------------
 int drl_learner_peer_export(drl_learner* h, void* handles, int64_t bytes) {
   DRL_TRY(check_handle(h));
+  DRL_LOCK(const_cast<drl_learner*>(h));
   if (!handles || bytes != 2 * (int64_t)sizeof(cudaIpcMemHandle_t)) { set_error("peer_export: expected a %d-byte buffer", (int)(2 * sizeof(cudaIpcMemHandle_t))); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
   if (!h->comm) {
@@ -663,6 +697,7 @@ int drl_learner_peer_export(drl_learner* h, void* handles, int64_t bytes) {
 
 int drl_learner_peer_import(drl_learner* h, int32_t rank, int32_t world, const void* all_handles, int64_t bytes) {
   DRL_TRY(check_handle(h));
+  DRL_LOCK(const_cast<drl_learner*>(h));
   if (world < 2 || world > kMaxPeers || rank < 0 || rank >= world) { set_error("peer_import: bad rank %d / world %d (max %d)", rank, world, kMaxPeers); return DRL_ERR_INVALID; }
   if (!all_handles || bytes != (int64_t)world * 2 * (int64_t)sizeof(cudaIpcMemHandle_t)) { set_error("peer_import: expected world x %d bytes", (int)(2 * sizeof(cudaIpcMemHandle_t))); return DRL_ERR_INVALID; }
   if (!h->comm) { set_error("peer_import before peer_export"); return DRL_ERR_STATE; }
@@ -689,7 +724,13 @@ int drl_learner_peer_import(drl_learner* h, int32_t rank, int32_t world, const v
     h->plan.t.epoch[p] = reinterpret_cast<uint32_t*>(comm + h->off_epoch);
     h->plan.t.err[p] = reinterpret_cast<uint32_t*>(comm + h->off_err);
   }
-  DRL_CUDA_CHECK(cudaHostGetDevicePointer((void**)&h->plan.t.err[rank], h->h_peer_err, 0));   // own entry: host-visible
+  DRL_CUDA_CHECK(cudaHostGetDevicePointer((void**)&h->plan.t.err_host, h->h_peer_err, 0));   // host-visible copy
+  {
+    const char* e = getenv("DRL_B200_PEER_TIMEOUT_S");
+    double sec = e ? atof(e) : 600.0;
+    if (!(sec > 0.0)) sec = 600.0;
+    h->plan.t.timeout_ns = (unsigned long long)(sec * 1e9);
+  }
   h->plan.rank = rank;
   h->plan.world = world;
   h->plan.nblk = h->peer_nblk;
@@ -703,6 +744,8 @@ int drl_learner_peer_import(drl_learner* h, int32_t rank, int32_t world, const v
   po.wait_epoch = h->plan.t.epoch[rank];
   po.wait_world = world;
   po.wait_err = h->plan.t.err[rank];
+  po.wait_err_host = h->plan.t.err_host;
+  po.wait_timeout_ns = h->plan.t.timeout_ns;
   po.wait_parts = kPeerParts;
   // graphs captured so far do not contain the exchange
   for (auto& g : h->graph_step) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
@@ -713,6 +756,7 @@ int drl_learner_peer_import(drl_learner* h, int32_t rank, int32_t world, const v
 
 int drl_learner_peer_disable(drl_learner* h) {
   DRL_TRY(check_handle(h));
+  DRL_LOCK(const_cast<drl_learner*>(h));
   DRL_TRY(set_device(h));
   DRL_CUDA_CHECK(cudaDeviceSynchronize());
   for (void* p : h->peer_opened) cudaIpcCloseMemHandle(p);
@@ -728,6 +772,7 @@ int drl_learner_peer_disable(drl_learner* h) {
 
 int drl_learner_stream(drl_learner* h, void** stream) {
   DRL_TRY(check_handle(h));
+  DRL_LOCK(const_cast<drl_learner*>(h));
   if (!stream) { set_error("null argument"); return DRL_ERR_INVALID; }
   *stream = h->compute;
   return DRL_OK;
@@ -735,6 +780,8 @@ int drl_learner_stream(drl_learner* h, void** stream) {
 
 int drl_learner_step_async(drl_learner* h, int32_t slot) {
   DRL_TRY(check_handle(h));
+  DRL_LOCK(const_cast<drl_learner*>(h));
+  DRL_TRY(check_not_failed(h));
   if (slot < 0 || slot >= (int)h->slots.size()) { set_error("slot %d out of range", slot); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
   return run_step(h, slot);
@@ -743,7 +790,10 @@ int drl_learner_step_async(drl_learner* h, int32_t slot) {
 static int collect(drl_learner* h, int row, drl_step_out* out) {
   DRL_CUDA_CHECK(cudaEventSynchronize(h->ev_done_slot[row]));
   if (h->peer_on && h->h_peer_err && *h->h_peer_err) {
-    set_error("peer exchange: rank %d never reached the barrier (20 s)", (int)*h->h_peer_err - 1);
+    h->failed = true;
+    set_error("peer exchange: rank %d never reached the barrier within %.0f s (DRL_B200_PEER_TIMEOUT_S); this replica "
+              "skipped the update and is out of step with its peers: destroy the handle",
+              (int)*h->h_peer_err - 1, (double)h->plan.t.timeout_ns * 1e-9);
     return DRL_ERR_STATE;
   }
   if (out) {
@@ -764,6 +814,7 @@ static int collect(drl_learner* h, int row, drl_step_out* out) {
 
 int drl_learner_wait(drl_learner* h, drl_step_out* out) {
   DRL_TRY(check_handle(h));
+  DRL_LOCK(const_cast<drl_learner*>(h));
   if (!h->pending) { set_error("wait: no step in flight"); return DRL_ERR_STATE; }
   DRL_TRY(set_device(h));
   h->pending = false;
@@ -772,6 +823,7 @@ int drl_learner_wait(drl_learner* h, drl_step_out* out) {
 
 int drl_learner_wait_slot(drl_learner* h, int32_t slot, drl_step_out* out) {
   DRL_TRY(check_handle(h));
+  DRL_LOCK(const_cast<drl_learner*>(h));
   if (slot < 0 || slot >= (int)h->slots.size()) { set_error("slot %d out of range", slot); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
   if (slot == h->last_out) h->pending = false;
@@ -779,12 +831,15 @@ int drl_learner_wait_slot(drl_learner* h, int32_t slot, drl_step_out* out) {
 }
 
 int drl_learner_step(drl_learner* h, int32_t slot, drl_step_out* out) {
+  DRL_TRY(check_handle(h));
+  DRL_LOCK(h);
   DRL_TRY(drl_learner_step_async(h, slot));
   return drl_learner_wait(h, out);
 }
 
 int drl_learner_forward(drl_learner* h, int32_t slot, float* policy, float* value) {
   DRL_TRY(check_handle(h));
+  DRL_LOCK(const_cast<drl_learner*>(h));
   if (slot < 0 || slot >= (int)h->slots.size()) { set_error("slot %d out of range", slot); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
   Slot& s = h->slots[slot];
@@ -810,6 +865,7 @@ int drl_learner_forward(drl_learner* h, int32_t slot, float* policy, float* valu
 
 int drl_learner_taps(drl_learner* h, float* vs, float* clipped_rho, float* vs_plus_1, float* pg_advantage) {
   DRL_TRY(check_handle(h));
+  DRL_LOCK(const_cast<drl_learner*>(h));
   DRL_TRY(set_device(h));
   const size_t n = (size_t)h->B * (h->T - 2) * sizeof(float);
   DRL_CUDA_CHECK(cudaStreamSynchronize(h->compute));
@@ -822,6 +878,7 @@ int drl_learner_taps(drl_learner* h, float* vs, float* clipped_rho, float* vs_pl
 
 int drl_learner_read_buffer(drl_learner* h, const char* name, float* host_dst, int64_t n) {
   DRL_TRY(check_handle(h));
+  DRL_LOCK(const_cast<drl_learner*>(h));
   if (!name || !host_dst) { set_error("null argument"); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
   const size_t M = h->M, Mb = h->Mb, A = h->A;
@@ -851,6 +908,7 @@ int drl_learner_read_buffer(drl_learner* h, const char* name, float* host_dst, i
 int drl_learner_act(drl_learner* h, int32_t n, const uint8_t* state, const int32_t* previous_action,
                     const float* h_in, const float* c_in, float* policy, float* h_out, float* c_out) {
   DRL_TRY(check_handle(h));
+  DRL_LOCK(const_cast<drl_learner*>(h));
   if (n < 1 || n > h->M) { set_error("act: n must be in [1, %d]", h->M); return DRL_ERR_INVALID; }
   if (!state || !previous_action || !h_in || !c_in) { set_error("act: null input pointer"); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
@@ -878,6 +936,7 @@ int drl_learner_act(drl_learner* h, int32_t n, const uint8_t* state, const int32
 int drl_learner_profile_step(drl_learner* h, int32_t slot, char* names, int64_t names_len, float* ms,
                              int32_t max_kernels, int32_t* count) {
   DRL_TRY(check_handle(h));
+  DRL_LOCK(const_cast<drl_learner*>(h));
   if (slot < 0 || slot >= (int)h->slots.size()) { set_error("slot %d out of range", slot); return DRL_ERR_INVALID; }
   if (!names || !ms || !count) { set_error("null argument"); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
@@ -898,6 +957,7 @@ int drl_learner_profile_step(drl_learner* h, int32_t slot, char* names, int64_t 
 
 int drl_learner_last_step_ms(drl_learner* h, float* ms) {
   DRL_TRY(check_handle(h));
+  DRL_LOCK(const_cast<drl_learner*>(h));
   if (!ms) { set_error("null argument"); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
   DRL_CUDA_CHECK(cudaEventSynchronize(h->ev_stop));
@@ -907,6 +967,7 @@ int drl_learner_last_step_ms(drl_learner* h, float* ms) {
 
 int drl_learner_launches_per_step(const drl_learner* h, int32_t* n) {
   DRL_TRY(check_handle(h));
+  DRL_LOCK(const_cast<drl_learner*>(h));
   if (!n) { set_error("null argument"); return DRL_ERR_INVALID; }
   // forward + V-trace/loss kernel + backward + 2 optimizer kernels (valid after the first step)
   *n = forward_launch_count() + 1 + backward_launch_count() + 2;

@@ -48,9 +48,13 @@ __global__ void __launch_bounds__(256) rmsprop_apply_kernel(OptState o) {
   __shared__ float s_scale;
   // data-parallel: barrier 1 of the peer exchange -- every peer has delivered its slice of the summed gradients and
   // its partial norms into this rank's buffers (peer.cu)
-  if (o.wait_flags)
+  // A failed barrier (time-out, now or in an earlier step) makes the update a no-op: parameters, slots and the
+  // step's scalars keep their values and the host reports the error (peer_sync.cuh).
+  if (o.wait_flags) {
+    const PeerErr perr{o.wait_err, o.wait_err_host, o.wait_timeout_ns};
     for (int part = 0; part < o.wait_parts; ++part)
-      wait_peers(o.wait_flags, 2 * part + 1, o.wait_world, o.wait_epoch[4 * part + 1], o.wait_err);
+      if (!wait_peers(o.wait_flags, 2 * part + 1, o.wait_world, o.wait_epoch[4 * part + 1], perr)) return;
+  }
   float acc = 0.f;
   for (int i = threadIdx.x; i < o.npart; i += blockDim.x) acc += o.norm_partials[i];
   acc = warp_sum(acc);

@@ -47,7 +47,9 @@ __global__ void __launch_bounds__(kPeerThreads) peer_reduce_kernel(PeerTable t, 
     __threadfence_system();
     st_release_sys(t.flags[threadIdx.x] + ph_ready * kMaxPeers + rank, e);
   }
-  wait_peers(t.flags[rank], ph_ready, world, e, t.err[rank]);
+  const PeerErr perr{t.err[rank], t.err_host, t.timeout_ns};
+  // failed state (now or earlier): leave every buffer, the step counter and the epochs untouched (see peer_sync.cuh)
+  if (!wait_peers(t.flags[rank], ph_ready, world, e, perr)) return;
 
   const int64_t n4_grad = o.n / 4;            // gradients (the norm is over these; the bucket tail holds loss sums)
   const int64_t per = (end4 - beg4 + world - 1) / world;

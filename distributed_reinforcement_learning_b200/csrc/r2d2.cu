@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include <string>
+#include <mutex>
 #include <vector>
 
 #include "layer_defs.cuh"
@@ -650,6 +651,8 @@ struct R2Slot {
 using namespace drl;
 
 struct drl_r2d2 {
+  std::recursive_mutex mu;   // every C-ABI entry point locks the handle (actor threads call parameter_sync -> get_params
+                             // on the learner's handle while the learner thread trains; ctypes drops the GIL)
   drl_r2d2_config cfg{};
   int B = 0, S = 0, A = 0, C = 1, mode = 2, Nt = 0;
   size_t frame = 0;
@@ -1081,12 +1084,14 @@ int drl_r2d2_destroy(drl_r2d2* h) {
 
 int drl_r2d2_param_count(const drl_r2d2* h, int64_t* n) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_r2d2*>(h)->mu);
   if (!n) { set_error("null argument"); return DRL_ERR_INVALID; }
   *n = h->pl.packed_total;
   return DRL_OK;
 }
 int drl_r2d2_set_params(drl_r2d2* h, int32_t which, const float* host_flat, int64_t n) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_r2d2*>(h)->mu);
   if (which != 0 && which != 1) { set_error("which must be 0 (main) or 1 (target)"); return DRL_ERR_INVALID; }
   if (!host_flat || n != h->pl.packed_total) { set_error("set_params: expected %lld floats, got %lld", (long long)h->pl.packed_total, (long long)n); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
@@ -1096,6 +1101,7 @@ int drl_r2d2_set_params(drl_r2d2* h, int32_t which, const float* host_flat, int6
 }
 int drl_r2d2_get_params(drl_r2d2* h, int32_t which, float* host_flat, int64_t n) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_r2d2*>(h)->mu);
   if (which != 0 && which != 1) { set_error("which must be 0 (main) or 1 (target)"); return DRL_ERR_INVALID; }
   if (!host_flat || n != h->pl.packed_total) { set_error("get_params: expected %lld floats", (long long)h->pl.packed_total); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
@@ -1104,6 +1110,7 @@ int drl_r2d2_get_params(drl_r2d2* h, int32_t which, float* host_flat, int64_t n)
 int drl_r2d2_set_opt_state(drl_r2d2* h, const float* host_m, const float* host_v, int64_t n, int64_t step,
                            float beta1_power, float beta2_power) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_r2d2*>(h)->mu);
   if (!host_m || !host_v || n != h->pl.packed_total) { set_error("set_opt_state: expected %lld floats", (long long)h->pl.packed_total); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
   DRL_TRY(upload_flat(h, h->adam_m, host_m));
@@ -1117,6 +1124,7 @@ int drl_r2d2_set_opt_state(drl_r2d2* h, const float* host_m, const float* host_v
 int drl_r2d2_get_opt_state(drl_r2d2* h, float* host_m, float* host_v, int64_t n, int64_t* step, float* beta1_power,
                            float* beta2_power) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_r2d2*>(h)->mu);
   if (n != h->pl.packed_total) { set_error("get_opt_state: expected %lld floats", (long long)h->pl.packed_total); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
   if (host_m) DRL_TRY(download_flat(h, h->adam_m, host_m));
@@ -1133,12 +1141,14 @@ int drl_r2d2_get_opt_state(drl_r2d2* h, float* host_m, float* host_v, int64_t n,
 }
 int drl_r2d2_get_grads(drl_r2d2* h, float* host_flat, int64_t n) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_r2d2*>(h)->mu);
   if (!host_flat || n != h->pl.packed_total) { set_error("get_grads: expected %lld floats", (long long)h->pl.packed_total); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
   return download_flat(h, h->grads, host_flat);
 }
 int drl_r2d2_main_to_target(drl_r2d2* h) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_r2d2*>(h)->mu);
   DRL_TRY(set_device(h));
   DRL_CUDA_CHECK(cudaMemcpyAsync(h->target, h->params, h->pl.padded_total * sizeof(float), cudaMemcpyDeviceToDevice, h->compute));
   pdl_break(h->compute);
@@ -1149,6 +1159,7 @@ int drl_r2d2_main_to_target(drl_r2d2* h) {
 int drl_r2d2_stage(drl_r2d2* h, int32_t slot, const uint8_t* state, const int32_t* previous_action, const int32_t* action,
                    const float* h0, const float* c0, const float* reward, const uint8_t* done, const float* weight) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_r2d2*>(h)->mu);
   if (slot < 0 || slot >= h->cfg.num_slots) { set_error("slot %d out of range", slot); return DRL_ERR_INVALID; }
   if (!state || !previous_action || !action || !h0 || !c0 || !reward || !done) { set_error("stage: null input pointer"); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
@@ -1162,30 +1173,35 @@ int drl_r2d2_stage(drl_r2d2* h, int32_t slot, const uint8_t* state, const int32_
 
 int drl_r2d2_step_async(drl_r2d2* h, int32_t slot) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_r2d2*>(h)->mu);
   if (slot < 0 || slot >= h->cfg.num_slots) { set_error("slot %d out of range", slot); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
   return run_step(h, slot);
 }
 int drl_r2d2_forward_backward(drl_r2d2* h, int32_t slot) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_r2d2*>(h)->mu);
   if (slot < 0 || slot >= h->cfg.num_slots) { set_error("slot %d out of range", slot); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
   return run_forward_backward(h, slot);
 }
 int drl_r2d2_grad_bucket(drl_r2d2* h, void** dev_ptr, int64_t* count) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_r2d2*>(h)->mu);
   if (dev_ptr) *dev_ptr = h->grads;
   if (count) *count = h->pl.padded_total + 4;
   return DRL_OK;
 }
 int drl_r2d2_apply(drl_r2d2* h, float grad_scale) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_r2d2*>(h)->mu);
   if (!(grad_scale > 0.f)) { set_error("apply: grad_scale must be > 0"); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
   return run_apply(h, grad_scale);
 }
 int drl_r2d2_wait(drl_r2d2* h, drl_r2d2_out* out, float* td_error) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_r2d2*>(h)->mu);
   if (!h->pending) { set_error("wait: no step in flight"); return DRL_ERR_STATE; }
   DRL_TRY(set_device(h));
   h->pending = false;
@@ -1210,6 +1226,7 @@ int drl_r2d2_step(drl_r2d2* h, int32_t slot, drl_r2d2_out* out, float* td_error)
 int drl_r2d2_td_error(drl_r2d2* h, int32_t n, const uint8_t* state, const int32_t* previous_action, const int32_t* action,
                       const float* h0, const float* c0, const float* reward, const uint8_t* done, float* td_error) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_r2d2*>(h)->mu);
   if (n < 1 || n > h->B) { set_error("td_error: n must be in [1, %d]", h->B); return DRL_ERR_INVALID; }
   if (!state || !previous_action || !action || !h0 || !c0 || !reward || !done || !td_error) { set_error("td_error: null pointer"); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
@@ -1226,6 +1243,7 @@ int drl_r2d2_td_error(drl_r2d2* h, int32_t n, const uint8_t* state, const int32_
 int drl_r2d2_act(drl_r2d2* h, int32_t n, const uint8_t* state, const int32_t* previous_action, const float* h_in,
                  const float* c_in, float* q_value, float* h_out, float* c_out) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_r2d2*>(h)->mu);
   const int M = h->B * h->S;
   if (n < 1 || n > M) { set_error("act: n must be in [1, %d]", M); return DRL_ERR_INVALID; }
   if (!state || !previous_action || !h_in || !c_in) { set_error("act: null pointer"); return DRL_ERR_INVALID; }
@@ -1250,6 +1268,7 @@ int drl_r2d2_act(drl_r2d2* h, int32_t n, const uint8_t* state, const int32_t* pr
 
 int drl_r2d2_taps(drl_r2d2* h, float* main_q, float* target_q, float* target_value, float* state_action_value) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_r2d2*>(h)->mu);
   DRL_TRY(set_device(h));
   if (h->last_b < 1) { set_error("taps: no step or td_error call has run"); return DRL_ERR_STATE; }
   DRL_CUDA_CHECK(cudaStreamSynchronize(h->compute));
@@ -1272,6 +1291,7 @@ int drl_r2d2_taps(drl_r2d2* h, float* main_q, float* target_q, float* target_val
 
 int drl_r2d2_read_buffer(drl_r2d2* h, const char* name, float* host_dst, int64_t n) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_r2d2*>(h)->mu);
   if (!name || !host_dst) { set_error("null argument"); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
   if (h->last_b < 1) { set_error("read_buffer: no step or td_error call has run"); return DRL_ERR_STATE; }
@@ -1298,6 +1318,7 @@ int drl_r2d2_read_buffer(drl_r2d2* h, const char* name, float* host_dst, int64_t
 int drl_r2d2_profile_step(drl_r2d2* h, int32_t slot, char* names, int64_t names_len, float* ms, int32_t max_kernels,
                           int32_t* count) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_r2d2*>(h)->mu);
   if (slot < 0 || slot >= h->cfg.num_slots) { set_error("slot %d out of range", slot); return DRL_ERR_INVALID; }
   if (!names || !ms || !count) { set_error("null argument"); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
@@ -1319,6 +1340,7 @@ int drl_r2d2_profile_step(drl_r2d2* h, int32_t slot, char* names, int64_t names_
 }
 int drl_r2d2_last_step_ms(drl_r2d2* h, float* ms) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_r2d2*>(h)->mu);
   if (!ms) { set_error("null argument"); return DRL_ERR_INVALID; }
   DRL_TRY(set_device(h));
   DRL_CUDA_CHECK(cudaEventSynchronize(h->ev_stop));
@@ -1327,12 +1349,14 @@ int drl_r2d2_last_step_ms(drl_r2d2* h, float* ms) {
 }
 int drl_r2d2_stream(drl_r2d2* h, void** stream) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_r2d2*>(h)->mu);
   if (!stream) { set_error("null argument"); return DRL_ERR_INVALID; }
   *stream = h->compute;
   return DRL_OK;
 }
 int drl_r2d2_launches_per_step(const drl_r2d2* h, int32_t* n) {
   DRL_TRY(check_handle(h));
+  std::lock_guard<std::recursive_mutex> _lk(const_cast<drl_r2d2*>(h)->mu);
   if (!n) { set_error("null argument"); return DRL_ERR_INVALID; }
   *n = h->launches;
   return DRL_OK;

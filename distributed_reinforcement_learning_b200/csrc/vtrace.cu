@@ -55,8 +55,9 @@ __device__ __forceinline__ void vtrace_trajectory(const VtraceCfg& cfg, const fl
     act = in.action[src];
     rew = clip_reward(in.reward[src], cfg.reward_clipping);
     gam = in.done[src] ? 0.f : cfg.discount;                               // agent/impala.py:51
-    pi_a = prow[act];
-    const float mu_a = in.mu[(size_t)src * A + act];
+    const bool act_ok = act >= 0 && act < A;                                // tf.one_hot: an out-of-range index selects
+    pi_a = act_ok ? prow[act] : 0.f;                                        // nothing (log(0), like the reference)
+    const float mu_a = act_ok ? in.mu[(size_t)src * A + act] : 0.f;
     const float log_rho = logf(pi_a) - logf(mu_a);                         // optimizer/vtrace.py:46-51
     const float rho = expf(log_rho);                                       // :74
     rhob = fminf(1.0f, rho);                                               // :75-80 (clip_rho = cs = min(1, rho))

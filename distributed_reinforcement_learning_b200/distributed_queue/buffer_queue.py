@@ -108,8 +108,12 @@ class FIFOQueue:
 
 
 class SumTree:
-    """buffer_queue.py:326-369 over the native float64 sum tree (``drl_per_*``): same attributes and methods; the
-    stored objects stay in a host list, the priorities live in the native tree."""
+    """buffer_queue.py:326-369 over the native float64 sum tree (``drl_per_*``).  The stored objects stay in a host
+    array (``data``), the priorities live in the native tree.  Exposed: ``capacity``, ``data``, ``n_entries`` and the
+    operations ``Memory`` needs; the reference's raw ``tree`` array / ``write`` cursor and its per-node
+    ``_propagate`` / ``_retrieve`` helpers are not (the native tree does that arithmetic, in the same float64 order).
+    ``Memory.e`` / ``Memory.a`` are the reference's constants (0.001 / 0.6) inside csrc/per.cu: overriding the class
+    attributes has no effect here."""
 
     def __init__(self, capacity):
         self.capacity = int(capacity)
@@ -221,8 +225,12 @@ class _RecordFIFO:
     def get_many(self, n, timeout=None):
         out = []
         with self._cv:
+            # records leave one at a time (so n may exceed the capacity, as with B serial tf dequeues), but a time-out
+            # loses nothing: what was taken so far goes back to the FRONT of the queue in its original order
             for _ in range(n):
                 if not self._cv.wait_for(lambda: len(self._items) > 0, timeout):
+                    self._items.extendleft(reversed(out))
+                    self._cv.notify_all()
                     raise N.TimeoutError_(N.DRL_ERR_TIMEOUT, "queue empty")
                 out.append(self._items.popleft())
                 self._cv.notify_all()

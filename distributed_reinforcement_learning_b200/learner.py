@@ -29,7 +29,7 @@ class NativeLearner:
                  discount_factor=0.99, start_learning_rate=0.0006, end_learning_rate=0.0,
                  learning_frame=1000000000, baseline_loss_coef=1.0, entropy_coef=0.05,
                  gradient_clip_norm=40.0, reward_clipping="abs_one", device=0, num_slots=2,
-                 use_cuda_graph=False, math_mode=0):
+                 use_cuda_graph=True, math_mode=0):
         if reward_clipping not in N.REWARD_CLIPPING:
             raise ValueError("reward_clipping must be one of %s" % sorted(N.REWARD_CLIPPING))   # utils.py:45
         h, w, c = input_shape

@@ -319,6 +319,16 @@ def test_record_queues_and_actor_buffers(native):
     assert len(ab.state) == 1 and ab.state[0].shape == (T, 84, 84, 4) and a.get_size() == 0
     with pytest.raises(native.TimeoutError_):
         a.sample_batch(timeout=0.05)                                      # empty -> blocks
+    # a time-out in the middle of a batch loses nothing: the records already taken go back to the front, in order
+    for v in (8, 9):
+        r.append_to_queue(0, np.zeros((T, 84, 84, 1), np.uint8), np.zeros(T, np.int32), np.full(T, v, np.int32),
+                          np.zeros(T, np.float32), np.zeros(T, bool), np.zeros((T, 64), np.float32), np.zeros((T, 64), np.float32))
+    r.batch_size = 3
+    with pytest.raises(native.TimeoutError_):
+        r.sample_batch(timeout=0.05)
+    assert r.get_size() == 2
+    r.batch_size = 2
+    assert [int(x[0]) for x in r.sample_batch().action] == [8, 9]
     lb = bq.LocalBuffer(capacity=5)
     for i in range(8):
         lb.append(i, i + 1, 0, 1, float(i), False)
