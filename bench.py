@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- IMPALA learner env-frames/sec on synthetic (T=20, B=32/GPU, 84x84x4) trajectories.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--scaling weak|strong]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
@@ -17,6 +17,10 @@ holds its own 32 trajectories and the gradient bucket is all-reduced (SUM, NCCL)
   cpu_baseline : the CPU oracle (oracle/impala_torch.py, float32, reference-shaped graph: 54 network
            copies, host float64 /255) timed on this box's host cores -- a torch restatement, not TF1.
 --impl reference runs only that CPU restatement with the same metric/config (TF 1.14 is not installable).
+--batch 4 is BASELINE configs[0] (the reference's own CPU-runnable case) for either arm; --scaling strong shards a
+fixed global batch of 256 trajectories over the N GPUs (configs[2]; the default, weak, keeps 32 per GPU).
+At N > 1 the line also carries "replicas_identical" (bitwise-equal parameters on every rank after the timed loops) and
+"reduce_matches_nccl" (the fused peer exchange's reduced bucket against an NCCL all-reduce of the saved local buckets).
 """
 import argparse
 import json
@@ -33,7 +37,34 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 T, A, L, B_PER_GPU = 20, 18, 256, 32
+STRONG_GLOBAL_BATCH = 256
 METRIC = "learner env-frames/sec (T=20,B=32/GPU,84x84x4)"
+
+
+def batch_per_gpu(args, world):
+    if args.scaling == "strong":
+        if STRONG_GLOBAL_BATCH % world:
+            raise SystemExit("--scaling strong: %d GPUs do not divide the global batch of %d" % (world, STRONG_GLOBAL_BATCH))
+        return STRONG_GLOBAL_BATCH // world
+    return args.batch
+
+
+def bench_config(args, world):
+    """The `config` object of BOTH arms (identical by construction: the driver compares them)."""
+    B = batch_per_gpu(args, world)
+    which = ("BASELINE configs[0]" if (B == 4 and world == 1) else "BASELINE configs[1]" if (B == 32 and world == 1)
+             else "BASELINE configs[2]" if world * B == 256 else "BASELINE configs[1] shape")
+    return {"workload": "IMPALA learner step (%s): B=%d trajectories/GPU, T=20, 84x84x4 uint8, A=18, LSTM 256; "
+                        "glorot random-init parameters" % (which, B),
+            "global_batch": world * B, "trajectory": T, "parallelism": "dp%d" % world,
+            "scaling_mode": args.scaling,
+            "l2": "inputs+activations+params ~%d MB/step %s 126 MB L2; two staging slots alternate"
+                  % (int(7.2 * B), ">" if 7.2 * B > 126 else "<"),
+            "arms": "ours: hand-written sm_100a kernels behind the C-ABI (csrc/libdrl_b200.so); reference: float32 "
+                    "torch-CPU restatement of the TF1 graph on the host cores (TF 1.14 is not installable), a bounded "
+                    "sample of min(global_batch, 32) trajectories per step"}
+
+
 MATH_MODES = {1: "FP32 FFMA (CUDA cores)",
               2: "tcgen05 kind::tf32, 3xTF32 split (A_lo*B_hi + A_hi*B_lo + A_hi*B_hi), fp32 TMEM accumulate",
               3: "tcgen05 kind::tf32 3xTF32, persistent warp-specialised kernels (dedicated epilogue warps)",
@@ -203,7 +234,7 @@ def usable_cores():
     return max(1, n)
 
 
-def cpu_reference(steps, warmup, B=B_PER_GPU):
+def cpu_reference(steps, warmup, B=B_PER_GPU, global_batch=None):
     import torch
     from oracle import impala_torch as it
     from oracle import synthetic
@@ -223,22 +254,26 @@ def cpu_reference(steps, warmup, B=B_PER_GPU):
     return dict(value=B * T / sec, unit="frames/s", cores=cores, kind="port", ms_per_step=sec * 1e3,
                 sample="%d timed steps (+%d warm-up) of the float32 torch-CPU restatement of the reference graph "
                        "(54 per-timestep network copies, host float64 /255, 2 serial V-trace scans, autograd, "
-                       "clip 40, TF1-RMSProp) at B=%d,T=%d" % (steps, warmup, B, T))
+                       "clip 40, TF1-RMSProp) at B=%d,T=%d%s" % (steps, warmup, B, T,
+                       "" if not global_batch or global_batch == B else
+                       " (a bounded sample: %d of the workload's %d trajectories per step)" % (B, global_batch)))
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
-    steps, warm = max(1, min(args.steps, 20)), max(1, min(args.warmup, 3))
-    cb = cpu_reference(steps, warm)
+    # same steps / warm-up as asked (the CPU step takes ~0.25 s at B=32: K=20, W=5 is ~6 s); a cap keeps an
+    # accidental --steps 1000 within a few minutes
+    steps, warm = max(1, min(args.steps, 200)), max(1, min(args.warmup, 20))
+    cfg = bench_config(args, world)
+    B = min(cfg["global_batch"], 32)
+    cb = cpu_reference(steps, warm, B, cfg["global_batch"])
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "frames/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "IMPALA learner step, B=32, T=20, 84x84x4 uint8 (BASELINE configs[1]); "
-                                   "CPU torch restatement of the TF1 reference (TF 1.14 not installable)",
-                       "global_batch": B_PER_GPU, "trajectory": T},
-            "cpu_baseline": cb, "gpu_launches": 0,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": cfg, "cpu_baseline": cb, "gpu_launches": 0,
             "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -265,7 +300,7 @@ def run_ours(args):
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
-    B, K, W = B_PER_GPU, args.steps, max(args.warmup, 3)
+    B, K, W = batch_per_gpu(args, world), args.steps, max(args.warmup, 3)
     M, Mb = B * T, B * (T - 2)
     # N = 1: the whole step is one CUDA graph.  N > 1, --collective peer (default): still one graph, the gradient
     # exchange runs as kernels over NVLink peer memory (csrc/peer.cu); --collective nccl: forward+backward and
@@ -319,14 +354,20 @@ def run_ours(args):
     for i in range(W):
         eng.step_async(i % 2)
     eng.wait()
+    # NVML is initialised BEFORE the barrier (nvmlInit costs milliseconds; started after it, rank 0 entered the timed
+    # region late and every other rank's first exchange kernel waited for it), then one more untimed step runs after
+    # the barrier so that all ranks enter the timed region from the same, synchronised state.
     sampler = ClockSampler(local) if rank == 0 else None
-    barrier()
     if sampler:
         sampler.start()
+    barrier()
+    eng.step_async(W % 2)
+    eng.wait()
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(ext)
     for i in range(K):
-        eng.step_async(i % 2)
+        eng.step_async((W + 1 + i) % 2)
     e1.record(ext)
     out = eng.wait()
     barrier()
@@ -361,8 +402,13 @@ def run_ours(args):
     ms_e2e = max(max_over_ranks(e2.elapsed_time(e3)), 0.0)
     ms_e2e = max(ms_e2e, wall_ms * 0.0)                   # event time is the reported one; wall kept for reference
 
+    # ---------------- N > 1: replicas identical? fused exchange == NCCL all-reduce of the local buckets? ----------
+    checks = {}
+    if world > 1:
+        checks = multi_gpu_checks(torch, dist, eng, hb, args, rank, world)
+
     # ---------------- per-kernel profile -> roofline of the dominant kernel ----------------
-    line_extra = {}
+    line_extra = dict(checks)
     if rank == 0:
         peaks = measured_peaks()
         eng.stage(0, *hb[0])
@@ -381,7 +427,7 @@ def run_ours(args):
                 "frac": ach / peaks["tf_sus"],
                 # fp32-grade results cost 3 tf32 MMAs per product and tf32 runs at half the bf16 rate:
                 "frac_of_3xtf32_ceiling": ach / (peaks["tf_sus"] / 6.0) if args.math_mode >= 2 else None,
-                "traffic": NCU_TRAFFIC_B32.get(name) if args.math_mode >= 2 else None,
+                "traffic": NCU_TRAFFIC_B32.get(name) if (args.math_mode == 2 and B == 32) else None,
                 "traffic_source": "profiles/r01_ncu_umma_full.md (ncu --set full, per launch)",
                 "peak_source": peaks["src"] + " bf16 sustained",
                 "math_mode": MATH_MODES[args.math_mode] + "; achieved = algorithmic 2MNK flops (counted once, "
@@ -395,27 +441,34 @@ def run_ours(args):
             line_extra["roofline_vtrace"] = vtrace_roofline(torch, peaks)
         except Exception as ex:      # pragma: no cover
             line_extra["roofline_vtrace"] = {"error": str(ex)}
+        try:
+            line_extra["roofline_vtrace_b32"] = vtrace_roofline(torch, peaks, Bv=32, reps=200)
+        except Exception as ex:      # pragma: no cover
+            line_extra["roofline_vtrace_b32"] = {"error": str(ex)}
         if args.cpu_baseline and world == 1:      # rank 0 at N=1 only
-            line_extra["cpu_baseline"] = cpu_reference(3, 1)
+            line_extra["cpu_baseline"] = cpu_reference(3, 1, min(B, 32), B)
     if world > 1:
         dist.barrier()           # peers' buffers stay mapped until everybody is done
     eng.close()
+    if rank == 0 and world == 1 and args.agent_api:
+        try:
+            line_extra["e2e_agent_api"] = agent_api_e2e(B, K, W, hb, args)
+        except Exception as ex:      # pragma: no cover
+            line_extra["e2e_agent_api"] = {"error": str(ex)}
     if rank == 0:
         fps = world * B * T / (ms_dev / K * 1e-3)
         fps_e2e = world * B * T / (ms_e2e / K * 1e-3)
+        cfg = bench_config(args, world)
         line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "IMPALA learner step (BASELINE configs[1]): B=32 trajectories/GPU, T=20, "
-                                       "84x84x4 uint8, A=18, LSTM 256; glorot random-init parameters",
-                           "global_batch": world * B, "trajectory": T, "parallelism": "dp%d" % world,
-                           "collective": (None if world == 1 else
-                                          "fused reduce-scatter/all-gather kernels over NVLink peer memory (CUDA IPC) "
-                                          "inside the step graph" if args.collective == "peer" else
-                                          "NCCL all_reduce(SUM) of the 16.6 MB bucket between two graphs"
-                                          if args.collective == "nccl" else "NONE (diagnostic, invalid)"),
-                           "l2": "inputs+activations+params ~230 MB/step > 126 MB L2; two staging slots alternate",
-                           "cuda_graph": bool(use_graph), "math_mode": MATH_MODES[args.math_mode]},
+                "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": cfg,
+                "impl_detail": {
+                    "collective": (None if world == 1 else
+                                   "fused reduce-scatter/all-gather kernels over NVLink peer memory (CUDA IPC) "
+                                   "inside the step graph" if args.collective == "peer" else
+                                   "NCCL all_reduce(SUM) of the 16.6 MB bucket between two graphs"
+                                   if args.collective == "nccl" else "NONE (diagnostic, invalid)"),
+                    "cuda_graph": bool(use_graph), "math_mode": MATH_MODES[args.math_mode]},
                 "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,
                         "ms_per_step": ms_e2e / K, "wall_ms_per_step": wall_ms / K,
                         "path": "pinned ring -> drl_learner_stage (copy stream) -> drl_learner_step_async -> "
@@ -432,10 +485,16 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def vtrace_roofline(torch, peaks, Bv=65536, Tv=18):
-    """drl_vtrace_from_softmax_dev on [B,18,18] softmaxes: algorithmic bytes per (b,t) element =
-    mu 72 + pi 72 + action 4 + discount 4 + reward 4 + value 4 + next_value 4 read, vs 4 + rho 4 written
-    = 172 B; 203 MB at B=65536 (> L2)."""
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of vtrace_from_softmax_pipe_kernel at [65536,18,18], from the
+# ncu --set full capture summarised in profiles/ (None until captured)
+NCU_TRAFFIC_VTRACE = None
+
+
+def vtrace_roofline(torch, peaks, Bv=65536, Tv=18, reps=20):
+    """drl_vtrace_from_softmax_dev on [B,18,18] softmaxes.  Algorithmic bytes per (b,t) element: mu 72 + pi 72 +
+    action 4 + discount 4 + reward 4 + value 4 read, vs 4 + rho 4 written = 168 B, plus next_values of which the
+    kernel reads only the LAST column (4 B per trajectory: optimizer/vtrace.py:62 uses next_values[:, -1] alone).
+    198 MB at B=65536 (> L2: HBM-bound); 97 KB at B=32 (the learner's own size: latency-bound, L2-resident)."""
     import ctypes as C
     from distributed_reinforcement_learning_b200 import _native as N
     dev = "cuda"
@@ -463,7 +522,7 @@ def vtrace_roofline(torch, peaks, Bv=65536, Tv=18):
     # The kernel streams 203 MB (> the 126 MB L2) per launch, so back-to-back launches keep missing L2; timing REPS
     # launches between one pair of events keeps the ~5 us event/launch overhead out of a ~40 us kernel.
     # A single flushed launch is timed as well (reported as kernel_ms_single_flushed).
-    REPS = 20
+    REPS = reps
     flush.zero_()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(st)
@@ -481,13 +540,95 @@ def vtrace_roofline(torch, peaks, Bv=65536, Tv=18):
         b.record(st)
         torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
-    nbytes = Bv * Tv * (2 * A * 4 + 5 * 4 + 8)
+    nbytes = Bv * Tv * (2 * A * 4 + 4 * 4 + 8) + Bv * 4
     ach = nbytes / (ms * 1e-3) / 1e9
+    single = float(np.median(ts))
+    big = nbytes > (126 << 20)
     return {"kernel": "vtrace_from_softmax_pipe_kernel", "bound": "hbm", "achieved": ach, "peak": peaks["hbm"],
-            "unit": "GB/s", "frac": ach / peaks["hbm"], "traffic": None, "peak_source": peaks["src"],
-            "bytes_per_launch": nbytes, "kernel_ms": ms, "kernel_ms_single_flushed": float(np.median(ts)),
-            "l2": "203 MB streamed per launch > 126 MB L2; %d back-to-back launches between one event pair" % REPS,
+            "unit": "GB/s", "frac": ach / peaks["hbm"],
+            "traffic": NCU_TRAFFIC_VTRACE if (big and Bv == 65536) else None, "peak_source": peaks["src"],
+            "bytes_per_launch": nbytes, "bytes_per_element": 168, "kernel_ms": ms, "kernel_ms_single_flushed": single,
+            "achieved_single_flushed": nbytes / (single * 1e-3) / 1e9,
+            "frac_single_flushed": nbytes / (single * 1e-3) / 1e9 / peaks["hbm"],
+            "l2": ("%.0f MB streamed per launch > 126 MB L2" % (nbytes / 1e6) if big else
+                   "%.0f KB per launch: L2-resident, launch-latency bound (reported for the learner's own size)"
+                   % (nbytes / 1e3)) + "; %d back-to-back launches between one event pair; single = one launch after "
+                  "an explicit 256 MB L2 flush" % REPS,
             "shape": [Bv, Tv, A]}
+
+
+def multi_gpu_checks(torch, dist, eng, hb, args, rank, world):
+    """(a) parameters bitwise identical on every rank after everything that ran so far; (b) one more step: the bucket
+    the update reads (the fused peer exchange's `reduced` buffer) against an NCCL all-reduce(SUM) of the ranks' saved
+    LOCAL gradient buckets.  The sums are formed in different orders (rank order here, NCCL's tree/ring there), so (b)
+    is checked to 1e-6 of the largest element, not bitwise."""
+    import zlib
+    dev = torch.device("cuda", eng.device)
+    p = eng.get_params()
+    crc = zlib.crc32(p.tobytes())
+    t = torch.tensor([crc], dtype=torch.int64, device=dev)
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t)
+    crcs = [int(x.item()) for x in parts]
+    res = {"replicas_identical": len(set(crcs)) == 1, "replica_param_crc32": crcs[0]}
+    if args.collective == "peer":
+        eng.stage(0, *hb[0])
+        eng.step(0)                                  # forward, backward, fused exchange, update
+        torch.cuda.synchronize()
+        local = eng.bucket_tensor().clone()          # this rank's own gradient sums (the backward pass left them there)
+        reduced = eng.reduced_tensor().clone()
+        dist.all_reduce(local, op=dist.ReduceOp.SUM)
+        scale = float(local.abs().max().item())
+        err = float((local - reduced).abs().max().item()) / max(scale, 1e-30)
+        ok = torch.tensor([1 if err <= 1e-6 else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        res.update(reduce_matches_nccl=bool(int(ok.item())), reduce_vs_nccl_max_rel_err=err)
+        p2 = eng.get_params()
+        t = torch.tensor([zlib.crc32(p2.tobytes())], dtype=torch.int64, device=dev)
+        dist.all_gather(parts, t)
+        res["replicas_identical"] = res["replicas_identical"] and len(set(int(x.item()) for x in parts)) == 1
+    else:
+        res["reduce_matches_nccl"] = None            # the exchange IS the NCCL all-reduce in this mode
+    return res
+
+
+def agent_api_e2e(B, K, W, hb, args):
+    """The number a train_impala.py user gets: the UNCHANGED learner loop body (train_impala.py:97-108) on the
+    reference-named classes -- queue.sample_batch(), np.stack of every field, impala.Agent.train (blocking, returns
+    the step's four scalars) -- with actor threads replaced by a pre-filled pinned ring that is topped up outside the
+    timed calls.  One step in flight (the reference's train is synchronous)."""
+    from distributed_reinforcement_learning_b200.agent import impala
+    from distributed_reinforcement_learning_b200.distributed_queue import buffer_queue
+    learner = impala.Agent(trajectory=T, input_shape=[84, 84, 4], num_action=A, lstm_hidden_size=L, discount_factor=0.99,
+                           start_learning_rate=0.0006, end_learning_rate=0.0, learning_frame=1000000000,
+                           baseline_loss_coef=1.0, entropy_coef=0.05, gradient_clip_norm=40.0,
+                           reward_clipping="abs_one", model_name="learner", learner_name="learner")
+    learner.set_session(None)
+    queue = buffer_queue.FIFOQueue(T, [84, 84, 4], A, 4 * B, B, 1, L)
+
+    def fill(i):
+        st, rw, ac, dn, mu, pa, h0, c0 = hb[i % 3]
+        for j in range(B):
+            queue.append_to_queue(0, st[j], None, rw[j], dn[j].view(np.bool_), mu[j], ac[j], pa[j], h0[j], c0[j])
+    ts = []
+    for i in range(W + K):
+        fill(i)
+        t0 = time.perf_counter()
+        batch = queue.sample_batch()
+        pi_loss, baseline_loss, entropy, learning_rate = learner.train(
+            state=np.stack(batch.state), reward=np.stack(batch.reward), action=np.stack(batch.action),
+            done=np.stack(batch.done), behavior_policy=np.stack(batch.behavior_policy),
+            previous_action=np.stack(batch.previous_action), initial_h=np.stack(batch.previous_h),
+            initial_c=np.stack(batch.previous_c))
+        if i >= W:
+            ts.append(time.perf_counter() - t0)
+    learner._engine.close()
+    queue.close()
+    ms = float(np.median(ts)) * 1e3
+    return {"value": B * T / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms, "ms_per_step_mean": float(np.mean(ts)) * 1e3,
+            "path": "FIFOQueue.sample_batch (pinned ring views) -> np.stack per field (zero-copy on ring views) -> "
+                    "impala.Agent.train -> drl_learner_stage + drl_learner_step (blocking, host wall clock, median of "
+                    "%d calls)" % K, "last": [float(pi_loss), float(baseline_loss), float(entropy), float(learning_rate)]}
 
 
 def main():
@@ -500,6 +641,12 @@ def main():
     ap.add_argument("--math-mode", type=int, default=2, choices=[1, 2, 3, 4],
                     help="1 = FP32 FFMA contractions, 2 = tcgen05 3xTF32 tensor-core contractions (default)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    ap.add_argument("--no-agent-api", dest="agent_api", action="store_false",
+                    help="skip the e2e_agent_api leg (the unchanged train_impala.py loop body on impala.Agent)")
+    ap.add_argument("--batch", type=int, default=B_PER_GPU,
+                    help="trajectories per GPU (32 = BASELINE configs[1], the default; 4 = configs[0])")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
+                    help="weak: --batch trajectories per GPU (default); strong: a global batch of 256 sharded over the GPUs")
     ap.add_argument("--collective", choices=["peer", "nccl", "none"], default="peer",
                     help="N > 1: fused peer-memory gradient exchange (default) or NCCL all_reduce; 'none' = no "
                          "exchange at all (diagnostic: N independent replicas, NOT a valid data-parallel step)")

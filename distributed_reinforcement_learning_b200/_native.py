@@ -109,6 +109,7 @@ def _load():
         "drl_learner_wait_slot": (C.c_int, [vp, i32, C.POINTER(StepOut)]),
         "drl_learner_forward_backward": (C.c_int, [vp, i32]),
         "drl_learner_grad_bucket": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i64)]),
+        "drl_learner_reduced_bucket": (C.c_int, [vp, C.POINTER(vp), C.POINTER(i64)]),
         "drl_learner_apply": (C.c_int, [vp]),
         "drl_learner_stream": (C.c_int, [vp, C.POINTER(vp)]),
         "drl_learner_peer_export": (C.c_int, [vp, vp, i64]),

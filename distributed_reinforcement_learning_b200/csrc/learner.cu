@@ -11,9 +11,19 @@
 #include <unordered_map>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: no link dependency, a no-op unless a profiler injects itself
+
 #include "kernels.h"
 
 namespace drl {
+
+// NVTX ranges (the reference has no tracing at all) around the host-side phases of a step:
+// stage (H2D enqueue), forward, vtrace_losses, backward, exchange, update.  Inside a CUDA-graph replay the phases are
+// one cudaGraphLaunch, so the ranges mark the capture / eager enqueue and the replay as a whole ("step(graph)").
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 static thread_local char g_err[1024] = {0};
 void set_error(const char* fmt, ...) {
@@ -229,11 +239,18 @@ int enqueue_forward(drl_learner* h, const Inputs& in, int B, int T, bool retile)
 
 int enqueue_forward_backward(drl_learner* h, int slot) {
   const Inputs& in = h->slots[slot].in;
-  DRL_TRY(enqueue_forward(h, in, h->B, h->T, true));
+  {
+    NvtxRange r("drl:forward");
+    DRL_TRY(enqueue_forward(h, in, h->B, h->T, true));
+  }
   VtraceCfg vc{h->cfg.discount_factor, h->cfg.baseline_loss_coef, h->cfg.entropy_coef, h->cfg.reward_clipping};
   prof_mark(h->compute, "vtrace_losses");
-  DRL_TRY(vtrace_losses(h->compute, vc, h->act.policy, h->act.value, in, h->vt, h->bwd.dlogits, h->bwd.dv, h->B,
-                        h->T, h->A));
+  {
+    NvtxRange r("drl:vtrace_losses");
+    DRL_TRY(vtrace_losses(h->compute, vc, h->act.policy, h->act.value, in, h->vt, h->bwd.dlogits, h->bwd.dv, h->B,
+                          h->T, h->A));
+  }
+  NvtxRange r("drl:backward");
   DRL_TRY(net_backward(streams_of(h), h->pl, h->params, h->wimg, h->bucket, in, h->act, h->bwd, h->B, h->T, h->mode));
   return DRL_OK;
 }
@@ -245,12 +262,17 @@ int enqueue_apply(drl_learner* h, int out_row, bool local_only = false) {
   o_local.out = o_peer.out = h->d_out + 8 * out_row;
   if (h->peer_on && !local_only) {
     prof_mark(h->compute, "peer_exchange");
-    DRL_TRY(peer_exchange(h->compute, h->plan, 0, 0, h->pl.padded_total / 4 + 1, true));   // grads + loss sums
+    {
+      NvtxRange r("drl:exchange");
+      DRL_TRY(peer_exchange(h->compute, h->plan, 0, 0, h->pl.padded_total / 4 + 1, true));   // grads + loss sums
+    }
     prof_mark(h->compute, "optimizer(rmsprop)");
+    NvtxRange r("drl:update");
     DRL_TRY(optimizer_update_only(h->compute, o_peer));
     prof_mark(h->compute, "end");
   } else {
     prof_mark(h->compute, "optimizer(norm+rmsprop)");
+    NvtxRange r("drl:update");
     DRL_TRY(optimizer_apply(h->compute, o_local));
     prof_mark(h->compute, "end");
   }
@@ -331,6 +353,7 @@ int run_step(drl_learner* h, int slot) {
       DRL_CUDA_CHECK(cudaGraphInstantiate(&h->graph_step[slot], g, 0));
       cudaGraphDestroy(g);
     }
+    NvtxRange r("drl:step(graph)");
     DRL_CUDA_CHECK(cudaGraphLaunch(h->graph_step[slot], h->compute));
   } else {
     DRL_TRY(enqueue_forward_backward(h, slot));
@@ -625,6 +648,7 @@ int drl_learner_stage(drl_learner* h, int32_t slot, const uint8_t* state, const 
     return DRL_ERR_INVALID;
   }
   DRL_TRY(set_device(h));
+  NvtxRange nvtx_r("drl:stage");
   Slot& s = h->slots[slot];
   const size_t BT = (size_t)h->B * h->T;
   // do not overwrite a slot the compute stream is still reading
@@ -658,6 +682,14 @@ int drl_learner_grad_bucket(drl_learner* h, void** dev_ptr, int64_t* count) {
   DRL_TRY(check_handle(h));
   DRL_LOCK(const_cast<drl_learner*>(h));
   if (dev_ptr) *dev_ptr = h->bucket;
+  if (count) *count = h->pl.padded_total + 4;
+  return DRL_OK;
+}
+
+int drl_learner_reduced_bucket(drl_learner* h, void** dev_ptr, int64_t* count) {
+  DRL_TRY(check_handle(h));
+  DRL_LOCK(h);
+  if (dev_ptr) *dev_ptr = h->peer_on ? static_cast<void*>(h->comm) : static_cast<void*>(h->bucket);
   if (count) *count = h->pl.padded_total + 4;
   return DRL_OK;
 }

@@ -253,6 +253,18 @@ class NativeLearner:
             self._ext_stream = torch.cuda.ExternalStream(self.stream_ptr(), device="cuda:%d" % self.device)
         return self._bucket
 
+    def reduced_tensor(self):
+        """torch view (no copy) of the bucket the update reads (the peer exchange's ``reduced`` buffer, else the
+        all-reduced gradient bucket) -- for checks against a library all-reduce of the saved local buckets."""
+        import torch
+        p, n = C.c_void_p(), C.c_int64()
+        N.check(N.lib.drl_learner_reduced_bucket(self._h, C.byref(p), C.byref(n)))
+
+        class _View:
+            __cuda_array_interface__ = {"shape": (int(n.value),), "typestr": "<f4",
+                                        "data": (int(p.value), False), "version": 2}
+        return torch.as_tensor(_View(), device="cuda:%d" % self.device)
+
     def _allreduce_bucket(self):
         import torch
         import torch.distributed as dist

@@ -126,6 +126,11 @@ int drl_learner_wait_slot(drl_learner* h, int32_t slot, drl_step_out* out);
 int drl_learner_forward_backward(drl_learner* h, int32_t slot);
 int drl_learner_grad_bucket(drl_learner* h, void** dev_ptr, int64_t* count);
 int drl_learner_apply(drl_learner* h);          /* async; follow with drl_learner_wait */
+/* (new) Device pointer of the bucket the update reads: the peer exchange's `reduced` buffer when that exchange is
+ * on, else the gradient bucket itself (already all-reduced by the caller).  Same shape as drl_learner_grad_bucket.
+ * Lets a harness compare the fused exchange with a library all-reduce of the saved local buckets (bench.py,
+ * tests/test_gpu_multi.py). */
+int drl_learner_reduced_bucket(drl_learner* h, void** dev_ptr, int64_t* count);
 /* (new) Gradient exchange over NVLink peer memory, fused with the global-norm partials, INSTEAD of an all-reduce of
  * the bucket (one process per GPU on one node; buffers shared through CUDA IPC).  Every rank calls peer_export (128
  * bytes out: IPC handles of its bucket and of its exchange buffer), the ranks all-gather those blobs by any means

@@ -26,15 +26,15 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out_dir, peer=False):
+def _worker(rank, world, port, out_dir, peer=False, Bt=B):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     from distributed_reinforcement_learning_b200.learner import shard_range
-    batch, params, cfg = parity.make_case(B, T, A, seed=77)
-    lo, hi = shard_range(rank, world, B)
+    batch, params, cfg = parity.make_case(Bt, T, A, seed=77)
+    lo, hi = shard_range(rank, world, Bt)
     sh = synthetic.slice_batch(batch, lo, hi)
     eng = parity.native_learner(sh, params, cfg, device=rank)
     eng.stage(0, *[sh[k] for k in synthetic.TRAIN_FIELDS])
@@ -42,6 +42,12 @@ def _worker(rank, world, port, out_dir, peer=False):
         eng.enable_peer_exchange()          # the exchange becomes part of the step (csrc/peer.cu)
     out = eng.step(0)                       # forward_backward -> all_reduce(SUM) -> apply
     grads, params1 = eng.get_grads(), eng.get_params()
+    if peer:                                # the fused exchange's result vs an NCCL all-reduce of the saved local buckets
+        torch.cuda.synchronize()
+        local, reduced = eng.bucket_tensor().clone(), eng.reduced_tensor().clone()
+        dist.all_reduce(local, op=dist.ReduceOp.SUM)
+        err = float((local - reduced).abs().max()) / max(float(local.abs().max()), 1e-30)
+        assert err <= 1e-6, "rank %d: fused exchange differs from the NCCL all-reduce of the local buckets: %g" % (rank, err)
     out2 = eng.step(0)                      # a second step: barrier epochs, buffer reuse
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), grads=grads, params=params1, params2=eng.get_params(),
              losses=np.array([out["pi_loss"], out["baseline_loss"], out["entropy"], out["grad_norm"]]),
@@ -73,7 +79,7 @@ def test_two_gpu_allreduce_step_equals_single_replica(native, tmp_path):
     assert np.max(np.abs((r0["params"] - p0) - (p1 - p0))) <= 1e-3 * np.max(np.abs(p1 - p0))
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_fused_peer_exchange_equals_nccl_path(native, tmp_path, world):
     """The exchange as kernels over NVLink peer memory (CUDA IPC; csrc/peer.cu) inside the step graph: all ranks end
     with bit-identical replicas, and gradients / losses / parameters equal the NCCL all-reduce path over two steps."""
@@ -83,8 +89,9 @@ def test_fused_peer_exchange_equals_nccl_path(native, tmp_path, world):
     d_nccl, d_peer = tmp_path / "nccl", tmp_path / "peer"
     d_nccl.mkdir()
     d_peer.mkdir()
-    mp.spawn(_worker, args=(world, _free_port(), str(d_nccl), False), nprocs=world, join=True)
-    mp.spawn(_worker, args=(world, _free_port(), str(d_peer), True), nprocs=world, join=True)
+    Bt = max(B, world)                                                # one trajectory per rank at world 8
+    mp.spawn(_worker, args=(world, _free_port(), str(d_nccl), False, Bt), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(d_peer), True, Bt), nprocs=world, join=True)
     n0 = np.load(d_nccl / "rank0.npz")
     p0 = np.load(d_peer / "rank0.npz")
     for r in range(1, world):
@@ -96,7 +103,7 @@ def test_fused_peer_exchange_equals_nccl_path(native, tmp_path, world):
     else:
         assert parity.rel_err(p0["grads"], n0["grads"]) < 1e-6        # NCCL's summation order differs for W > 2
     assert np.allclose(p0["losses"], n0["losses"], rtol=1e-6) and np.allclose(p0["losses2"], n0["losses2"], rtol=1e-5)
-    upd = np.max(np.abs(n0["params2"] - it.flatten_params(parity.make_case(B, T, A, seed=77)[1])))
+    upd = np.max(np.abs(n0["params2"] - it.flatten_params(parity.make_case(Bt, T, A, seed=77)[1])))
     assert np.max(np.abs(p0["params2"] - n0["params2"])) <= 1e-4 * upd
 
 
