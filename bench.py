@@ -68,7 +68,9 @@ def bench_config(args, world):
 MATH_MODES = {1: "FP32 FFMA (CUDA cores)",
               2: "tcgen05 kind::tf32, 3xTF32 split (A_lo*B_hi + A_hi*B_lo + A_hi*B_hi), fp32 TMEM accumulate",
               3: "tcgen05 kind::tf32 3xTF32, persistent warp-specialised kernels (dedicated epilogue warps)",
-              4: "tcgen05 kind::tf32 3xTF32 with TMA-fed conv2/conv3 forward (tensor loads of value + tf32-remainder planes)"}
+              4: "tcgen05 kind::tf32 3xTF32 with TMA-fed conv2/conv3 forward (tensor loads of value + tf32-remainder planes)",
+              5: "tcgen05 kind::f16 with 16-bit split operands (A_lo*B_hi + A_hi*B_lo + A_hi*B_hi, fp32 TMEM accumulate; "
+                 "bf16 hi/lo planes, uint8 frames exact in fp16)"}
 
 
 def synth_batch(B, seed):
@@ -426,7 +428,8 @@ def run_ours(args):
                 "kernel": name, "bound": "tensor", "achieved": ach, "peak": peaks["tf_sus"], "unit": "TFLOP/s",
                 "frac": ach / peaks["tf_sus"],
                 # fp32-grade results cost 3 tf32 MMAs per product and tf32 runs at half the bf16 rate:
-                "frac_of_3xtf32_ceiling": ach / (peaks["tf_sus"] / 6.0) if args.math_mode >= 2 else None,
+                "frac_of_3xtf32_ceiling": ach / (peaks["tf_sus"] / 6.0) if args.math_mode in (2, 3, 4) else None,
+                "frac_of_3x16bit_ceiling": ach / (peaks["tf_sus"] / 3.0) if args.math_mode == 5 else None,
                 "traffic": NCU_TRAFFIC_B32.get(name) if (args.math_mode == 2 and B == 32) else None,
                 "traffic_source": "profiles/r01_ncu_umma_full.md (ncu --set full, per launch)",
                 "peak_source": peaks["src"] + " bf16 sustained",
@@ -638,8 +641,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="launch kernels directly instead of CUDA graphs")
-    ap.add_argument("--math-mode", type=int, default=2, choices=[1, 2, 3, 4],
-                    help="1 = FP32 FFMA contractions, 2 = tcgen05 3xTF32 tensor-core contractions (default)")
+    ap.add_argument("--math-mode", type=int, default=5, choices=[1, 2, 3, 4, 5],
+                    help="1 = FP32 FFMA contractions, 2 = tcgen05 3xTF32, 5 = tcgen05 kind::f16 with 16-bit split operands (default)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--no-agent-api", dest="agent_api", action="store_false",
                     help="skip the e2e_agent_api leg (the unchanged train_impala.py loop body on impala.Agent)")

@@ -88,7 +88,10 @@ constexpr int kLstmSplits = 8;   // slabs allocated for the LSTM split-K partial
 #define DRL_DEFAULT_PDL_LEVEL 0   // programmatic dependent launch (common.cuh); see DESIGN.md for the measurements
 #endif
 #ifndef DRL_DEFAULT_MATH_MODE
-#define DRL_DEFAULT_MATH_MODE 2
+#define DRL_DEFAULT_MATH_MODE 2          // Ape-X / A3C / R2D2 handles
+#endif
+#ifndef DRL_DEFAULT_MATH_MODE_IMPALA
+#define DRL_DEFAULT_MATH_MODE_IMPALA 5   // IMPALA handle: tcgen05 kind::f16 with 16-bit split operands (gemm_umma16.cuh)
 #endif
 
 // Per-kernel device timing (learner.cu): when a profile run is active, prof_mark records a CUDA event

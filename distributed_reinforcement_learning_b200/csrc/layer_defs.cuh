@@ -6,6 +6,7 @@
 
 #include "gemm_simt.cuh"
 #include "gemm_umma.cuh"
+#include "gemm_umma16.cuh"
 #include "gemm_tma.cuh"
 #include "gemm_umma_persist.cuh"
 #include "kernels.h"
@@ -45,6 +46,20 @@ using U64L = UmmaCfg<64, 2, 2, 4, 1>;
 using U128L = UmmaCfg<128, 3, 1, 8, 1>;
 using U256L = UmmaCfg<256, 2, 1, 8, 1>;
 
+// math mode 5: 16-bit split operands (gemm_umma16.cuh).  One format per GEMM (f16 x bf16 traps).  bf16 keeps fp32's
+// exponent range (gradients span many decades); fp16 has three more mantissa bits but underflows gradually below ~1e-4
+// and saturates at 65504 -- it is used where one operand is EXACT in it (the uint8 frames of conv1) and the other is
+// an O(0.1) weight.
+using Fmt16 = umma16::BF16;     // every GEMM whose operands are fp32 activations / gradients / weights
+using FmtC1 = umma16::F16;      // conv1: uint8 frames (exact) x weights
+using X32L = Umma16Cfg<32, 4, 2, 4, 1, FmtC1, FmtC1>;        // conv1 fwd: whole K = 256 resident
+using X64L = Umma16Cfg<64, 2, 2, 4, 1, Fmt16, Fmt16>;        // conv2 / conv3 fwd: 48 KB per K = 64 stage, 2 CTAs per SM
+using X64W = Umma16Cfg<64, 2, 2, 4, 0, Fmt16, Fmt16>;        // conv2 / conv3 weight gradients (both operands gathered)
+using X256L = Umma16Cfg<256, 2, 1, 8, 1, Fmt16, Fmt16>;      // lstm fwd: 96 KB per stage
+using X256W = Umma16Cfg<256, 2, 1, 8, 0, Fmt16, Fmt16>;      // lstm weight gradient
+using X128D = Umma16Cfg<128, 3, 1, 8, 1, Fmt16, Fmt16>;      // lstm data gradient: 64 KB per stage
+using X256D = Umma16Cfg<256, 2, 1, 8, 1, Fmt16, Fmt16>;      // dCol GEMMs (K = 64: one stage)
+
 // math mode 3 (experimental): the persistent, fully warp-specialised variant of each tensor-core configuration
 template <class U> struct PersistOf;
 template <> struct PersistOf<U32> { using type = UmmaPCfg<32, 5, 8>; };
@@ -62,11 +77,18 @@ template <> struct PersistOf<U256L> { using type = UmmaPCfg<256, 2, 8>; };
     prof_mark(s, name);                                      \
     if (mode == 3) {                                         \
       DRL_TRY((launch_gemm_umma_persist<typename PersistOf<UCfg>::type>(s, __VA_ARGS__))); \
-    } else if (mode == 2) {                                  \
+    } else if (mode == 2 || mode == 5) {                     \
       DRL_TRY((launch_gemm_umma<UCfg>(s, __VA_ARGS__)));     \
     } else {                                                 \
       DRL_TRY((launch_gemm_simt<SCfg>(s, __VA_ARGS__)));     \
     }                                                        \
+    ++n;                                                     \
+  } while (0)
+// a GEMM on the 16-bit split core (math mode 5)
+#define GEMM16(name, XCfg, ...)                              \
+  do {                                                       \
+    prof_mark(s, name);                                      \
+    DRL_TRY((launch_gemm_umma16<XCfg>(s, __VA_ARGS__)));     \
     ++n;                                                     \
   } while (0)
 // same, for GEMMs whose B operand is a weight matrix: the tensor-core cores read its pre-tiled image (blp)
@@ -113,9 +135,11 @@ static SplitPlan plan_conv1_wgrad(int Mb, int mode) {
   return mode >= 2 ? plan_split(Mb * 400, 2, 32, 2) : plan_split(Mb * 400, cdiv(256, CfgWg1::BM), 16, 2);
 }
 static SplitPlan plan_conv2_wgrad(int Mb, int mode) {
+  if (mode == 5) return plan_split(Mb * 81, 4, 64, 2);
   return mode >= 2 ? plan_split(Mb * 81, 4, 32, 2) : plan_split(Mb * 81, cdiv(512, CfgBig::BM), 16, 2);
 }
 static SplitPlan plan_conv3_wgrad(int Mb, int mode) {
+  if (mode == 5) return plan_split(Mb * 49, 5, 64, 2);
   return mode >= 2 ? plan_split(Mb * 49, 5, 32, 2) : plan_split(Mb * 49, cdiv(576, CfgBig::BM), 16, 2);
 }
 

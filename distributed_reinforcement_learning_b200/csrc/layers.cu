@@ -42,7 +42,7 @@ int backward_launch_count() { return g_bwd_launches; }
 size_t wgrad_partial_floats(int B, int T) {
   const int Mb = B * (T - 2);
   size_t mx = 0;
-  for (int mode = 1; mode <= 3; ++mode) {
+  for (int mode : {1, 2, 3, 5}) {
     mx = std::max(mx, (size_t)plan_conv1_wgrad(Mb, mode).splits * 257 * 32);
     mx = std::max(mx, (size_t)plan_conv2_wgrad(Mb, mode).splits * 513 * 64);
     mx = std::max(mx, (size_t)plan_conv3_wgrad(Mb, mode).splits * 577 * 64);
@@ -63,6 +63,16 @@ void weight_image_sizes(size_t (&b)[WeightImages::kCount]) {
 // Refresh the weight images (4 launches on the side stream + 1 for the two conv-forward images; ~60 MB written).
 // Must run after every parameter change.  Image 0 (conv1) is unused: conv1 is the first kernel of the step and its
 // weight tile is 1/5 of a stage.
+// math mode 5: the same seven images in the 16-bit K-major form (gemm_umma16.cuh); they fit into the same buffers
+int net_retile16(cudaStream_t s_rest, const ParamLayout& pl, const float* P, const WeightImages& wi) {
+  prof_mark(s_rest, "weight_retile");
+  DRL_TRY((launch_retile_b16<256, Fmt16>(s_rest, PlainB{P + pl.lstm_w, Geo::G4, 0}, Geo::G4, Geo::XK, wi.img[3])));
+  DRL_TRY((launch_retile_b16<128, Fmt16>(s_rest, PlainBT{P + pl.lstm_w, Geo::G4, 0}, Geo::FLAT + Geo::EMB, Geo::G4, wi.img[4])));
+  DRL_TRY((launch_retile_b16<256, Fmt16>(s_rest, PlainBT{P + pl.conv3_w, 64, 0}, 576, 64, wi.img[5])));
+  DRL_TRY((launch_retile_b16<256, Fmt16>(s_rest, PlainBT{P + pl.conv2_w, 64, 0}, 512, 64, wi.img[6])));
+  return DRL_OK;
+}
+
 int net_retile(cudaStream_t, cudaStream_t s_rest, const ParamLayout& pl, const float* P, const WeightImages& wi) {
   prof_mark(s_rest, "weight_retile");
   DRL_TRY((launch_retile_b<256>(s_rest, PlainB{P + pl.lstm_w, Geo::G4, 0}, Geo::G4, Geo::XK, wi.img[3])));
@@ -86,7 +96,16 @@ int net_forward(const Streams& st, const ParamLayout& pl, const float* P, const 
   s = side;
   // weight images of this step's parameters, all on the side stream: the conv2/conv3 forward ones first (main waits
   // for them behind conv1), the LSTM / dgrad ones behind the embedding table (joined before lstm_fwd)
-  if (retile && mode >= 2) {
+  const bool m16 = mode == 5;
+  if (retile && m16) {
+    prof_mark(s, "weight_retile");
+    DRL_TRY((launch_retile_b16<32, FmtC1>(s, PlainB{P + pl.conv1_w, 32, 0}, 32, 256, wi.img[0])));
+    if (st.par) DRL_CUDA_CHECK(cudaEventRecord(st.ev[2], side));          // conv1 waits for its (tiny) image
+    DRL_TRY((launch_retile_b16<64, Fmt16>(s, PlainB{P + pl.conv2_w, 64, 0}, 64, 512, wi.img[1])));
+    DRL_TRY((launch_retile_b16<64, Fmt16>(s, PlainB{P + pl.conv3_w, 64, 0}, 64, 576, wi.img[2])));
+    if (st.par) DRL_CUDA_CHECK(cudaEventRecord(st.ev[7], side));          // conv2 / conv3 images (main waits behind conv1)
+    n += 3;
+  } else if (retile && mode >= 2) {
     prof_mark(s, "weight_retile");
     DRL_TRY((launch_retile_b<64>(s, PlainB{P + pl.conv2_w, 64, 0}, 64, 512, wi.img[1])));
     DRL_TRY((launch_retile_b<64>(s, PlainB{P + pl.conv3_w, 64, 0}, 64, 576, wi.img[2])));
@@ -97,15 +116,25 @@ int net_forward(const Streams& st, const ParamLayout& pl, const float* P, const 
          emb_forward(s, P + pl.emb1_w, P + pl.emb1_b, P + pl.emb2_w, P + pl.emb2_b, act.e1, act.table, pl.A), 1);
   s = st.main;
   if (retile && mode >= 2) {
-    DRL_TRY(net_retile(st.main, side, pl, P, wi));
+    if (m16) DRL_TRY(net_retile16(side, pl, P, wi));
+    else DRL_TRY(net_retile(st.main, side, pl, P, wi));
     n += 4;
+  }
+  if (retile && m16 && st.par) {
+    DRL_CUDA_CHECK(cudaStreamWaitEvent(st.main, st.ev[2], 0));
+    pdl_break(st.main);
   }
   // conv1: u8 frames -> a1 [M,20,20,32]   (attention_CNN, model/impala_actor_critic.py:6)
   {
     Conv1A al{in.frames, map};
     PlainB bl{P + pl.conv1_w, 32, 0};
     EpConv1 ep{act.a1, 32, P + pl.conv1_b, tma ? act.a1_lo : nullptr};
-    GEMM("conv1_fwd", CfgN32, U32, al, bl, ep, M * 400, 32, 256, 1, 256, 0);
+    if (m16) {
+      PretiledB<PlainB> blp{wi.img[0], 256 / 64};
+      GEMM16("conv1_fwd", X32L, al, blp, ep, M * 400, 32, 256, 1, 256, 0);
+    } else {
+      GEMM("conv1_fwd", CfgN32, U32, al, bl, ep, M * 400, 32, 256, 1, 256, 0);
+    }
   }
   if (retile && mode >= 2 && st.par) {
     DRL_CUDA_CHECK(cudaStreamWaitEvent(st.main, st.ev[7], 0));
@@ -118,9 +147,10 @@ int net_forward(const Streams& st, const ParamLayout& pl, const float* P, const 
   } else {
     Conv2A al{act.a1, map};
     PlainB bl{P + pl.conv2_w, 64, 0};
-    PretiledB<PlainB> blp{wi.img[1], 512 / 32};
+    PretiledB<PlainB> blp{wi.img[1], m16 ? 512 / 64 : 512 / 32};
     EpBiasAct<true, true> ep{act.a2, 64, 0, P + pl.conv2_b, 0, 1.0f};
-    GEMM_W("conv2_fwd", CfgBig, U64L, al, bl, blp, ep, M * 81, 64, 512, 1, 512, 0);
+    if (m16) GEMM16("conv2_fwd", X64L, al, blp, ep, M * 81, 64, 512, 1, 512, 0);
+    else GEMM_W("conv2_fwd", CfgBig, U64L, al, bl, blp, ep, M * 81, 64, 512, 1, 512, 0);
   }
   // conv3 -> a3 [M,7,7,64] = flatten HWC [M,3136]   (:8-10)
   if (tma) {
@@ -129,9 +159,10 @@ int net_forward(const Streams& st, const ParamLayout& pl, const float* P, const 
   } else {
     Conv3A al{act.a2, map};
     PlainB bl{P + pl.conv3_w, 64, 0};
-    PretiledB<PlainB> blp{wi.img[2], 576 / 32};
+    PretiledB<PlainB> blp{wi.img[2], m16 ? 576 / 64 : 576 / 32};
     EpBiasAct<true, true> ep{act.a3, 64, 0, P + pl.conv3_b, 0, 1.0f};
-    GEMM_W("conv3_fwd", CfgBig, U64L, al, bl, blp, ep, M * 49, 64, 576, 1, 576, 0);
+    if (m16) GEMM16("conv3_fwd", X64L, al, blp, ep, M * 49, 64, 576, 1, 576, 0);
+    else GEMM_W("conv3_fwd", CfgBig, U64L, al, bl, blp, ep, M * 49, 64, 576, 1, 576, 0);
   }
   DRL_TRY(join_from_side(st, 1));
   // LSTM pre-activation z = [a3 | emb | h0] W  (split-K partial sums; bias added in the gate kernel) (:18-25)
@@ -141,9 +172,10 @@ int net_forward(const Streams& st, const ParamLayout& pl, const float* P, const 
     EpRaw<false> ep{act.zpart, Geo::G4, (size_t)M * Geo::G4, 1.0f, 0, Geo::G4};
     // FFMA: 4 splits of 57 x 16.  tcgen05: 128 x 256 tiles -> 5 x 4 output tiles x 7 splits of 17 x 32 = 140 CTAs (one wave)
     nsplit = (mode >= 2) ? 7 : 4;
-    const int kchunk = (mode >= 2) ? 544 : Geo::XK / 4;
-    PretiledB<PlainB> blp{wi.img[3], Geo::XK / 32};
-    GEMM_W("lstm_fwd", CfgMid, U256L, al, bl, blp, ep, M, Geo::G4, Geo::XK, nsplit, kchunk, kchunk);
+    const int kchunk = m16 ? 576 : (mode >= 2) ? 544 : Geo::XK / 4;      // 16-bit: 9 K tiles of 64 per split
+    PretiledB<PlainB> blp{wi.img[3], m16 ? Geo::XK / 64 : Geo::XK / 32};
+    if (m16) GEMM16("lstm_fwd", X256L, al, blp, ep, M, Geo::G4, Geo::XK, nsplit, kchunk, kchunk);
+    else GEMM_W("lstm_fwd", CfgMid, U256L, al, bl, blp, ep, M, Geo::G4, Geo::XK, nsplit, kchunk, kchunk);
   }
   KERNEL("lstm_gates_fwd",
          lstm_gates_forward(s, act.zpart, nsplit, P + pl.lstm_b, in.c0, act.gates, act.c1, act.tc1, act.h1, M, B,
@@ -173,6 +205,7 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, const
                  const Inputs& in, const Acts& act, const Bwd& bw, int B, int T, int mode) {
   PdlRegionOff pdl_region;   // DRL_B200_PDL=2: no early launches while the side stream competes for the same SMs
   if (mode == 4) mode = 2;
+  const bool m16 = mode == 5;
   cudaStream_t s = st.main;
   const cudaStream_t side = st.par ? st.side : st.main;
   const int M = B * T;
@@ -237,15 +270,17 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, const
     LstmAT al{act.a3, act.table, in.pa, in.h0, map};
     PlainB bl{bw.dz, Geo::G4, 0};
     EpRaw<true> ep{G + pl.lstm_w, Geo::G4, 0, 1.0f, Geo::XK, Geo::G4};
-    GEMM("lstm_wgrad", CfgBig, U256, al, bl, ep, Geo::XK, Geo::G4, Mb, 1, Mb, 0);   // 29 x 4 = 116 CTAs: one wave
+    if (m16) GEMM16("lstm_wgrad", X256W, al, bl, ep, Geo::XK, Geo::G4, Mb, 1, Mb, 0);
+    else GEMM("lstm_wgrad", CfgBig, U256, al, bl, ep, Geo::XK, Geo::G4, Mb, 1, Mb, 0);   // 29 x 4 = 116 CTAs: one wave
   }
   s = st.main;
   {  // d[a3 | emb] = dz W[:3392]^T  (h0, c0 are fed data: no gradient, agent/impala.py:38-39)
     PlainA al{bw.dz, Geo::G4, 0};
     PlainBT bl{P + pl.lstm_w, Geo::G4, 0};
     EpLstmDx ep{bw.da3, act.a3, bw.du};
-    PretiledB<PlainBT> blp{wi.img[4], Geo::G4 / 32};
-    GEMM_W("lstm_dgrad", CfgMid, U128L, al, bl, blp, ep, Mb, Geo::FLAT + Geo::EMB, Geo::G4, 1, Geo::G4, 0);
+    PretiledB<PlainBT> blp{wi.img[4], m16 ? Geo::G4 / 64 : Geo::G4 / 32};
+    if (m16) GEMM16("lstm_dgrad", X128D, al, blp, ep, Mb, Geo::FLAT + Geo::EMB, Geo::G4, 1, Geo::G4, 0);
+    else GEMM_W("lstm_dgrad", CfgMid, U128L, al, bl, blp, ep, Mb, Geo::FLAT + Geo::EMB, Geo::G4, 1, Geo::G4, 0);
   }
   // ---- action embedding + conv3 weight gradient (side) -------------------------------------
   DRL_TRY(fork_to_side(st, 4));
@@ -260,7 +295,8 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, const
     Conv3WA al{act.a2, map};
     PlainB bl{bw.da3, 64, 0};
     EpRaw<true> ep{bw.wg_part, 64, slab, 1.0f, 576, 64};
-    GEMM("conv3_wgrad", CfgBig, U64, al, bl, ep, 576, 64, Mb * 49, sp.splits, sp.kchunk, sp.kchunk);
+    if (m16) GEMM16("conv3_wgrad", X64W, al, bl, ep, 576, 64, Mb * 49, sp.splits, sp.kchunk, sp.kchunk);
+    else GEMM("conv3_wgrad", CfgBig, U64, al, bl, ep, 576, 64, Mb * 49, sp.splits, sp.kchunk, sp.kchunk);
     KERNEL("conv3_wgrad_reduce", splitk_reduce(s, bw.wg_part, slab, sp.splits, G + pl.conv3_w, slab), 1);
   }
   s = st.main;
@@ -273,8 +309,9 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, const
     // K = 64 (two K tiles) and 128 x 256 outputs per tile: epilogue-dominated, so the persistent kernel with
     // dedicated epilogue warps wins here (measured 0.067 vs 0.073 ms); elsewhere two CTAs per SM win.
     prof_mark(s, "conv3_dgrad");
-    PretiledB<PlainBT> blp{wi.img[5], 2};
-    DRL_TRY((launch_gemm_umma_persist<PersistOf<U256>::type>(s, al, blp, ep, Mb * 49, 576, 64, 1, 64, 0)));
+    PretiledB<PlainBT> blp{wi.img[5], m16 ? 1 : 2};
+    if (m16) DRL_TRY((launch_gemm_umma16<X256D>(s, al, blp, ep, Mb * 49, 576, 64, 1, 64, 0)));
+    else DRL_TRY((launch_gemm_umma_persist<PersistOf<U256>::type>(s, al, blp, ep, Mb * 49, 576, 64, 1, 64, 0)));
     prof_mark(s, "conv3_col2im");
     DRL_TRY(col2im_conv3(s, bw.dcol, act.a2, bw.da2, Mb));
     n += 2;
@@ -293,7 +330,8 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, const
     Conv2WA al{act.a1, map};
     PlainB bl{bw.da2, 64, 0};
     EpRaw<true> ep{bw.wg_part, 64, slab, 1.0f, 512, 64};
-    GEMM("conv2_wgrad", CfgBig, U64, al, bl, ep, 512, 64, Mb * 81, sp.splits, sp.kchunk, sp.kchunk);
+    if (m16) GEMM16("conv2_wgrad", X64W, al, bl, ep, 512, 64, Mb * 81, sp.splits, sp.kchunk, sp.kchunk);
+    else GEMM("conv2_wgrad", CfgBig, U64, al, bl, ep, 512, 64, Mb * 81, sp.splits, sp.kchunk, sp.kchunk);
     KERNEL("conv2_wgrad_reduce", splitk_reduce(s, bw.wg_part, slab, sp.splits, G + pl.conv2_w, slab), 1);
   }
   s = st.main;
@@ -302,8 +340,9 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, const
     PlainBT bl{P + pl.conv2_w, 64, 0};               // B(k = co, n = (ky,kx,ci)) = W[n*64 + co]
     EpRaw<false> ep{bw.dcol, 512, 0, 1.0f, 0, 512};
     prof_mark(s, "conv2_dgrad");                      // persistent kernel: 0.079 vs 0.091 ms
-    PretiledB<PlainBT> blp{wi.img[6], 2};
-    DRL_TRY((launch_gemm_umma_persist<PersistOf<U256>::type>(s, al, blp, ep, Mb * 81, 512, 64, 1, 64, 0)));
+    PretiledB<PlainBT> blp{wi.img[6], m16 ? 1 : 2};
+    if (m16) DRL_TRY((launch_gemm_umma16<X256D>(s, al, blp, ep, Mb * 81, 512, 64, 1, 64, 0)));
+    else DRL_TRY((launch_gemm_umma_persist<PersistOf<U256>::type>(s, al, blp, ep, Mb * 81, 512, 64, 1, 64, 0)));
     prof_mark(s, "conv2_col2im");
     DRL_TRY(col2im_conv2(s, bw.dcol, act.a1, bw.da1, Mb));
     n += 2;

@@ -384,7 +384,7 @@ int drl_debug_trace(void* dev_buf) {
   DRL_CUDA_CHECK(cudaDeviceSynchronize());
   return DRL_OK;
 }
-const char* drl_version(void) { return "drl_b200 0.3 (sm_100a; tcgen05 3xTF32 gather-GEMM, FP32-FFMA core, NVLink peer exchange; IMPALA, Ape-X, R2D2, A3C learners)"; }
+const char* drl_version(void) { return "drl_b200 0.4 (sm_100a; tcgen05 kind::f16 split-16 / 3xTF32 gather-GEMMs, FP32-FFMA core, NVLink peer exchange; IMPALA, Ape-X, R2D2, A3C learners)"; }
 
 int drl_device_count(void) {
   int n = 0;
@@ -408,16 +408,16 @@ int drl_learner_create(const drl_learner_config* cfg, drl_learner** out) {
     set_error("reward_clipping must be DRL_REWARD_ABS_ONE or DRL_REWARD_SOFT_ASYMMETRIC");   // utils.py:45
     return DRL_ERR_INVALID;
   }
-  if (cfg->math_mode < 0 || cfg->math_mode > 4) {
-    set_error("math_mode must be 0 (default), 1 (FP32 FFMA), 2 (tcgen05 3xTF32), 3 (same, persistent kernels) or "
-              "4 (same as 2 with TMA-fed conv2/conv3 forward)");
+  if (cfg->math_mode < 0 || cfg->math_mode > 5) {
+    set_error("math_mode must be 0 (default), 1 (FP32 FFMA), 2 (tcgen05 3xTF32), 3 (same, persistent kernels), "
+              "4 (same as 2 with TMA-fed conv2/conv3 forward) or 5 (tcgen05 kind::f16 with 16-bit split operands)");
     return DRL_ERR_INVALID;
   }
   if (drl_device_count() <= cfg->device) { set_error("CUDA device %d not available (no CPU fallback)", cfg->device); return DRL_ERR_CUDA; }
 
   drl_learner* h = new drl_learner();
   h->cfg = *cfg;
-  h->mode = (cfg->math_mode == 0) ? DRL_DEFAULT_MATH_MODE : cfg->math_mode;
+  h->mode = (cfg->math_mode == 0) ? DRL_DEFAULT_MATH_MODE_IMPALA : cfg->math_mode;
   if (h->cfg.num_slots < 1) h->cfg.num_slots = 2;
   h->B = cfg->batch; h->T = cfg->trajectory; h->A = cfg->num_action;
   h->M = h->B * h->T; h->Mb = h->B * (h->T - 2);
