@@ -116,7 +116,9 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
-__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+// 1 / (1 + e^-x) with the approximate-reciprocal division (<= 2 ulp): the IEEE division's FCHK + slow-path subroutine costs
+// hundreds of cycles per element in the gate kernels (see div255 in loaders.cuh for the measurement)
+__device__ __forceinline__ float sigmoidf_acc(float x) { return __fdividef(1.0f, 1.0f + expf(-x)); }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }

@@ -1,0 +1,316 @@
+// conv1_tma.cuh -- conv1 of the attention_CNN (model/impala_actor_critic.py:6: 8x8 stride 4 over 84x84x4 uint8 frames ->
+// 20x20x32, ReLU) as a FRAME-RESIDENT, TMA-fed, warp-specialised tcgen05 kernel (math mode 5).
+//
+// The generic gather-GEMM spends conv1's time in per-CTA fixed costs: 2000 CTAs of one 128-row tile each (K = 256 only),
+// every one paying barrier/TMEM set-up, a cold first gather and a serial epilogue, and every frame byte is gathered 4x
+// through the LSU (8x8 windows at stride 4 overlap).  Here one persistent CTA per SM walks over whole frames:
+//
+//   TMA warp      one tensor load per frame: the raw 84x84x4 bytes (28,224 B) -> shared memory, double-buffered
+//                 (tensor map {16 B, 21, 84, frames}, box = one frame; the (t,b) -> b*T+t remap of the caller's batch-major
+//                 trajectory buffer is just the box coordinate); the fp16 hi/lo weight image (32 KB) is fetched once
+//   8 converter   expand the im2col FROM SHARED MEMORY: thread (pixel, ky) reads the 32 contiguous bytes of one window row,
+//   warps         turns them into 32 fp16 (exact: PRMT + HSUB2) and writes 4 swizzled 16-byte chunks of a K-major
+//                 SWIZZLE_128B operand stage [128 pixels x 64 features]; 16 stages per frame (4 M tiles x 4 K chunks)
+//                 through a ring of 6
+//   MMA warp      4 tcgen05.mma (kind::f16, M128 N64 K16) per stage: the B tile is [W_hi ; W_lo] stacked along N (the two
+//                 planes of the weight image are adjacent, i.e. ONE 64-row K-major tile), so A x W_hi lands in columns
+//                 0-31 and A x W_lo in columns 32-63 of one of two TMEM accumulators and the epilogue adds the halves --
+//                 half the instructions of issuing the two products separately (an N = 32 MMA costs 44 cycles, an N = 64
+//                 one 48: tools/microbench/mma_rate.cu); tcgen05.commit frees the stage / publishes the accumulator
+//   4 epilogue    TMEM -> registers -> /255 (true fp32 divide, agent/impala.py:133) + bias + ReLU -> coalesced stores of
+//   warps         the a1 rows, overlapped with the next tile's conversion and MMAs
+//
+// Algorithmic traffic per frame: 28,224 B read once (TMA) + 51,200 B of a1 written; shared memory sees the 4x im2col
+// amplification instead of L2 (102 KB read, 205 KB written, 205 KB read by the tensor core per frame).
+#pragma once
+#include <cuda.h>
+#include <stdlib.h>
+
+#include <map>
+#include <tuple>
+
+#include "gemm_tma.cuh"
+#include "gemm_umma16.cuh"
+#include "loaders.cuh"
+
+namespace drl {
+
+namespace umma {
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+      : "memory");
+}
+}  // namespace umma
+
+struct Conv1Tma {
+  static constexpr int FRAME = Geo::FRAME;            // 28,224 bytes
+  static constexpr int PIX = Geo::C1H * Geo::C1W;     // 400 output pixels per frame
+  static constexpr int MT = 4;                        // 128-row M tiles per frame (the last one holds 16 pixels)
+  static constexpr int KC = 4;                        // K chunks of 64 features (two window rows ky) per M tile
+  static constexpr int NS = 6;                        // operand stages in the ring
+  static constexpr int STAGE_BYTES = 128 * 128;       // 128 pixels x 64 fp16
+  static constexpr int RAW_STRIDE = 28672;            // frame buffer pitch (128-byte multiple)
+  static constexpr int W_BYTES = 4 * 2 * 32 * 128;    // 4 K tiles x [hi | lo] x 32 rows x 128 B = 32 KB
+  static constexpr int CONV_WARPS = 8, EPI_WARPS = 4;
+  static constexpr int W_TMA = CONV_WARPS + EPI_WARPS, W_MMA = W_TMA + 1;   // warps 0-7 convert, 8-11 epilogue, 12 TMA, 13 MMA
+  static constexpr int NT = (W_MMA + 1) * 32;         // 448 threads
+  static constexpr int OFF_RAW = NS * STAGE_BYTES;
+  static constexpr int OFF_W = OFF_RAW + 2 * RAW_STRIDE;
+  static constexpr int OFF_EPI = OFF_W + W_BYTES;
+  static constexpr int OFF_AUX = OFF_EPI + EPI_WARPS * kEpiStageBytes;
+  static constexpr int OFF_DBG = OFF_AUX + 512;        // 4 roles x 96 clock samples (debug timeline, tools/conv1_timeline.py)
+  static constexpr int SMEM_BYTES = OFF_DBG + 4 * 96 * 8 + 1024;
+  static constexpr int TMEM_COLS = 128;               // two accumulators of 64 columns ([A x W_hi | A x W_lo])
+};
+
+template <class EP>
+__global__ void __launch_bounds__(Conv1Tma::NT, 1)
+conv1_fwd_tma_kernel(const __grid_constant__ CUtensorMap fmap, const uint8_t* __restrict__ wimage, const EP ep, RowMap map,
+                     int nframes, int flags) {
+  pdl_prologue();
+  using C = Conv1Tma;
+  using TA = Umma16Tile<128, true>;
+  using TB = Umma16Tile<32, true>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* raw = smem + C::OFF_RAW;
+  uint8_t* wsm = smem + C::OFF_W;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + C::OFF_AUX);   // [NS]
+  uint64_t* a_empty = a_full + C::NS;                                  // [NS]
+  uint64_t* raw_full = a_empty + C::NS;                                // [2]
+  uint64_t* raw_empty = raw_full + 2;                                  // [2]
+  uint64_t* acc_full = raw_empty + 2;                                  // [2]
+  uint64_t* acc_empty = acc_full + 2;                                  // [2]
+  uint64_t* w_full = acc_empty + 2;                                    // [1]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_full + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // debug timeline: when the trace buffer is armed with magic 0xC0171 in word 8001, lane 0 of each role keeps clock64()
+  // samples in shared memory (no global traffic while running) and CTA 0 dumps them behind word 8002 at the end
+  long long* dbg = reinterpret_cast<long long*>(smem + C::OFF_DBG);
+  unsigned long long* const trbuf = g_trace_tu;
+  const bool tracing = trbuf != nullptr && trbuf[8001] == 0xC0171ull && blockIdx.x == 0;
+  int dn = 0;
+#define C1_TR(role) do { if (tracing && dn < 96) dbg[(role) * 96 + dn++] = clock64(); } while (0)
+  if (tracing) for (int i = tid; i < 4 * 96; i += blockDim.x) dbg[i] = 0;
+  if (tid == 0) {
+    for (int s = 0; s < C::NS; ++s) {
+      umma::mbar_init(&a_full[s], C::CONV_WARPS * 32);
+      umma::mbar_init(&a_empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      umma::mbar_init(&raw_full[b], 1);
+      umma::mbar_init(&raw_empty[b], C::CONV_WARPS * 32);
+      umma::mbar_init(&acc_full[b], 1);
+      umma::mbar_init(&acc_empty[b], C::EPI_WARPS * 32);
+    }
+    umma::mbar_init(w_full, 1);
+    umma::fence_barrier_init();
+  }
+  if (warp == C::W_MMA) umma::tmem_alloc<C::TMEM_COLS>(tmem_ptr);
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp < C::CONV_WARPS) {
+    // ================= CONVERTERS: raw frame bytes -> fp16 K-major operand stages =================
+    const int p_local = tid & 127, kyl = tid >> 7;      // pixel row of the tile; which of the chunk's two window rows
+    uint32_t it = 0;
+    int fi = 0;
+    for (int mf = blockIdx.x; mf < nframes; mf += gridDim.x, ++fi) {
+      const int slot = fi & 1;
+      umma::mbar_wait(&raw_full[slot], (fi >> 1) & 1);
+      const uint8_t* fr = raw + slot * C::RAW_STRIDE;
+#pragma unroll 1
+      for (int mt = 0; mt < C::MT; ++mt) {
+        const int p = mt * 128 + p_local;
+        const bool live = p < C::PIX;
+        const int oy = p / Geo::C1W, ox = p - oy * Geo::C1W;
+        const uint8_t* win = fr + (4 * oy + kyl) * (Geo::IW * Geo::IC) + 16 * ox;
+#pragma unroll 1
+        for (int c = 0; c < C::KC; ++c, ++it) {
+          const int s = it % C::NS;
+          umma::mbar_wait(&a_empty[s], ((it / C::NS) & 1) ^ 1);
+          if (tid == 0) C1_TR(0);
+          if (live) {
+            const uint4* src = reinterpret_cast<const uint4*>(win + (2 * c) * (Geo::IW * Geo::IC));
+            const uint4 r0 = src[0], r1 = src[1];
+            uint8_t* row = smem + s * C::STAGE_BYTES + p_local * 128;
+            const int sw = p_local & 7, q0 = kyl * 4;
+            uint2 h;
+            uint4 o;
+            h = umma16::u8x4_to_h4(r0.x); o.x = h.x; o.y = h.y; h = umma16::u8x4_to_h4(r0.y); o.z = h.x; o.w = h.y;
+            *reinterpret_cast<uint4*>(row + (((q0 + 0) ^ sw) << 4)) = o;
+            h = umma16::u8x4_to_h4(r0.z); o.x = h.x; o.y = h.y; h = umma16::u8x4_to_h4(r0.w); o.z = h.x; o.w = h.y;
+            *reinterpret_cast<uint4*>(row + (((q0 + 1) ^ sw) << 4)) = o;
+            h = umma16::u8x4_to_h4(r1.x); o.x = h.x; o.y = h.y; h = umma16::u8x4_to_h4(r1.y); o.z = h.x; o.w = h.y;
+            *reinterpret_cast<uint4*>(row + (((q0 + 2) ^ sw) << 4)) = o;
+            h = umma16::u8x4_to_h4(r1.z); o.x = h.x; o.y = h.y; h = umma16::u8x4_to_h4(r1.w); o.z = h.x; o.w = h.y;
+            *reinterpret_cast<uint4*>(row + (((q0 + 3) ^ sw) << 4)) = o;
+          }
+          umma::fence_proxy_async();
+          umma::mbar_arrive(&a_full[s]);
+          if (tid == 0) C1_TR(0);
+        }
+      }
+      umma::mbar_arrive(&raw_empty[slot]);        // this thread no longer reads the frame buffer
+    }
+  } else if (warp < C::W_TMA) {
+    // ================= EPILOGUE (warps 8..11: TMEM lane quarter = warp & 3) =================
+    const int quarter = warp & 3;
+    uint8_t* stg = smem + C::OFF_EPI + quarter * kEpiStageBytes;
+    uint32_t tile = 0;
+    for (int mf = blockIdx.x; mf < nframes; mf += gridDim.x) {
+      const int row_base = mf * C::PIX, row_end = row_base + C::PIX;
+      for (int mt = 0; mt < C::MT; ++mt, ++tile) {
+        const int buf = tile & 1;
+        umma::mbar_wait(&acc_full[buf], (tile >> 1) & 1);
+        umma::tc_fence_after();
+        if (warp == C::CONV_WARPS && lane == 0) C1_TR(2);
+        float v[32], w[32];
+        umma::tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * 64), v);
+        umma::tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * 64 + 32), w);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += w[i];     // hi product + lo product
+        umma::tc_fence_before();
+        umma::mbar_arrive(&acc_empty[buf]);
+        if (flags & 1) {
+          // experiment: no output at all
+        } else if (flags & 48) {   // experiments: 16 = multiply by 1/255 instead of dividing; 32 = compute but do not store
+          const int m = row_base + mt * 128 + quarter * 32 + lane;
+          if (m < row_end) {
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float o[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float x = v[4 * j + q];
+                const float y = (flags & 16) ? x * (1.0f / 255.0f) : x / 255.0f;
+                o[q] = fmaxf(y + __ldg(ep.bias + 4 * j + q), 0.f);
+                acc += o[q];
+              }
+              if (!(flags & 32)) *reinterpret_cast<float4*>(ep.c + (size_t)m * 32 + 4 * j) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+            if ((flags & 32) && acc == 123456.789f) ep.c[0] = acc;     // keep the arithmetic alive
+          }
+        } else if (flags & 4) {   // experiment: every lane stores its own row, no staging through shared memory
+          const int m = row_base + mt * 128 + quarter * 32 + lane;
+          if (m < row_end) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float o[4] = {v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]};
+              ep.template store<4>(0, m, 4 * j, o);
+            }
+          }
+        } else
+        epilogue_store_32x32(ep, stg, lane, 0, row_base + mt * 128 + quarter * 32, 0, row_end, 32, v);
+        if (warp == C::CONV_WARPS && lane == 0) C1_TR(2);
+      }
+    }
+  } else if (warp == C::W_TMA) {
+    // ================= TMA PRODUCER =================
+    if (lane == 0) {
+      umma::prefetch_tensormap(&fmap);
+      umma::mbar_arrive_expect_tx(w_full, C::W_BYTES);
+      umma::bulk_g2s(wsm, wimage, C::W_BYTES, w_full);
+      int fi = 0;
+      for (int mf = blockIdx.x; mf < nframes; mf += gridDim.x, ++fi) {
+        const int slot = fi & 1;
+        umma::mbar_wait(&raw_empty[slot], ((fi >> 1) & 1) ^ 1);
+        C1_TR(3);
+        umma::mbar_arrive_expect_tx(&raw_full[slot], C::FRAME);
+        umma::tma_load_4d(raw + slot * C::RAW_STRIDE, &fmap, 0, 0, 0, map.src(mf), &raw_full[slot]);
+      }
+    }
+  } else {
+    // ================= MMA ISSUER =================
+    constexpr uint32_t idesc = umma16::make_idesc16(64, umma16::F16::kFormat, umma16::F16::kFormat, false, false);
+    umma::mbar_wait(w_full, 0);
+    uint32_t it = 0, tile = 0;
+    for (int mf = blockIdx.x; mf < nframes; mf += gridDim.x) {
+      for (int mt = 0; mt < C::MT; ++mt, ++tile) {
+        const int buf = tile & 1;
+        umma::mbar_wait(&acc_empty[buf], ((tile >> 1) & 1) ^ 1);
+        umma::tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(buf * 64);
+        for (int c = 0; c < C::KC; ++c, ++it) {
+          const int s = it % C::NS;
+          umma::mbar_wait(&a_full[s], (it / C::NS) & 1);
+          umma::tc_fence_after();
+          if (lane == 0) C1_TR(1);
+          if (umma::elect_one()) {
+            const uint64_t da_base = umma::make_desc(0, TA::LBO, TA::SBO, TA::LAYOUT_TYPE);
+            const uint64_t db_base = umma::make_desc(0, TB::LBO, TB::SBO, TB::LAYOUT_TYPE);
+            const uint64_t a = umma::desc_at(da_base, umma::smem_u32(smem + s * C::STAGE_BYTES));
+            const uint64_t b = umma::desc_at(db_base, umma::smem_u32(wsm + c * (2 * TB::BYTES)));   // [W_hi ; W_lo]: 64 rows
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint64_t ko = (uint64_t)(j * 32 >> 4);
+              umma16::mma_f16(d, a + ko, b + ko, idesc, (c > 0 || j > 0) ? 1u : 0u);
+            }
+            umma::mma_commit(&a_empty[s]);
+            if (c == C::KC - 1) umma::mma_commit(&acc_full[buf]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+    umma::tc_fence_before();
+  }
+  __syncthreads();
+  if (tracing) {
+    for (int i = tid; i < 4 * 96; i += blockDim.x) trbuf[8002 + i] = (unsigned long long)dbg[i];
+  }
+#undef C1_TR
+  if (warp == C::W_MMA) {
+    umma::tc_fence_after();
+    umma::tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+// frames: the staging slot's uint8 [nframes, 84, 84, 4] buffer (caller's batch-major order)
+inline int conv1_frame_map(const uint8_t* frames, int nframes, CUtensorMap* out) {
+  TmaEncodeTiledFn enc = tma_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is not available in this driver"); return DRL_ERR_CUDA; }
+  const cuuint64_t dims[4] = {16, 21, 84, (cuuint64_t)nframes};
+  const cuuint64_t strides[3] = {16, 336, (cuuint64_t)Geo::FRAME};
+  const cuuint32_t box[4] = {16, 21, 84, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<uint8_t*>(frames), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for the frame map", (int)r); return DRL_ERR_CUDA; }
+  return DRL_OK;
+}
+
+template <class EP>
+inline int launch_conv1_fwd_tma(cudaStream_t s, const uint8_t* frames, int nframes, const RowMap& map, const uint8_t* wimage,
+                                const EP& ep) {
+  using Key = std::tuple<const uint8_t*, int>;
+  static thread_local std::map<Key, CUtensorMap> cache;
+  const Key key{frames, nframes};
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    CUtensorMap m;
+    DRL_TRY(conv1_frame_map(frames, nframes, &m));
+    it = cache.emplace(key, m).first;
+  }
+  static bool attr_done = false;
+  auto kern = conv1_fwd_tma_kernel<EP>;
+  if (!attr_done) {
+    DRL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Conv1Tma::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int grid = std::min(nframes, device_sm_count());
+  static const int flags = getenv("DRL_C1_FLAGS") ? atoi(getenv("DRL_C1_FLAGS")) : 0;   // experiments (see the kernel)
+  DRL_CUDA_CHECK((launch_k(kern, grid, Conv1Tma::NT, Conv1Tma::SMEM_BYTES, s, it->second, wimage, ep, map, nframes, flags)));
+  return DRL_OK;
+}
+
+}  // namespace drl

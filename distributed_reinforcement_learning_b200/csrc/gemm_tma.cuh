@@ -149,7 +149,7 @@ conv_fwd_tma_kernel(const __grid_constant__ ConvTmaMaps<Cfg::TAPS> maps, const u
         const int s = it % NSTAGE;
         umma::mbar_wait(&full[s], (it / NSTAGE) & 1);
         umma::tc_fence_after();
-        if (lane == 0) {
+        if (umma::elect_one()) {
           const uint32_t st = umma::smem_u32(smem + s * Cfg::STAGE_BYTES);
           const uint32_t a_hi = st, a_lo = st + Cfg::A_BYTES, b_hi = st + 2 * Cfg::A_BYTES, b_lo = b_hi + Cfg::B_BYTES;
 #pragma unroll

@@ -105,6 +105,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// One lane of a converged warp, chosen by the hardware (elect.sync).  Unlike `lane == 0`, the compiler knows the branch
+// holds exactly one thread and keeps the tcgen05 operands (descriptors, TMEM address) in uniform registers with a plain
+// R2UR; with `lane == 0` it wrapped EVERY tcgen05.mma in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (cuobjdump), which
+// together with the per-MMA descriptor arithmetic cost ~120-165 cycles per MMA against 44-128 for the instruction itself
+// (tools/microbench/mma_rate.cu).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// descriptor = constant part (everything but the start address) + (shared-memory byte address >> 4)
+__device__ __forceinline__ uint64_t desc_at(uint64_t base, uint32_t saddr) { return base + (uint64_t)(saddr >> 4); }
+
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): descriptor version 1 (sm_100), base_offset 0,
 // layout_type 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
@@ -234,6 +247,15 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 // shared-memory tile instead (16-byte chunks XOR-swizzled by row & 7: conflict-free both ways), so that 8 lanes
 // cover one 128-byte row segment and an instruction touches 4 lines.  The functor sees the same (m, n) pairs.
 constexpr int kEpiStageBytes = 32 * 32 * 4;
+// An epilogue functor may provide `bias4(z, n)` + `store4b(z, m, n, o, bias)`: the per-column bias of a lane is the same
+// for all 8 rows it stores, so it is fetched ONCE per 32x32 block instead of once per element.  (Measured on the conv1
+// kernel: the streaming stores of the output evict the bias line from L1, each of the 8 row iterations then paid an L2
+// round trip for it, and the epilogue of one 128x32 tile took 11,000 cycles -- tools/conv1_timeline.py.)
+template <class EP, class = void>
+struct ep_has_bias4 : std::false_type {};
+template <class EP>
+struct ep_has_bias4<EP, std::void_t<decltype(std::declval<const EP&>().bias4(0, 0))>> : std::true_type {};
+
 template <class EP>
 __device__ __forceinline__ void epilogue_store_32x32(const EP& ep, uint8_t* stg, int lane, int z, int row0, int col0,
                                                      int M, int N, const float (&v)[32]) {
@@ -243,15 +265,21 @@ __device__ __forceinline__ void epilogue_store_32x32(const EP& ep, uint8_t* stg,
         make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
   __syncwarp();
   const int c = lane & 7, rr = lane >> 3;
+  const int n = col0 + c * 4;
+  float4 bias = zero4();
+  if constexpr (ep_has_bias4<EP>::value) {
+    if (n + 3 < N) bias = ep.bias4(z, n);
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = i * 4 + rr;
     const float4 o4 = *reinterpret_cast<const float4*>(stg + r * 128 + ((c ^ (r & 7)) << 4));
-    const int m = row0 + r, n = col0 + c * 4;
+    const int m = row0 + r;
     if (m < M) {
       const float o[4] = {o4.x, o4.y, o4.z, o4.w};
       if (n + 3 < N) {
-        ep.template store<4>(z, m, n, o);
+        if constexpr (ep_has_bias4<EP>::value) ep.store4b(z, m, n, o, bias);
+        else ep.template store<4>(z, m, n, o);
       } else {
 #pragma unroll
         for (int q = 0; q < 4; ++q)
@@ -533,7 +561,7 @@ gemm_umma_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, int
       const uint32_t ph = (t / STAGES) & 1;
       umma::mbar_wait(&full[s], ph);
       umma::tc_fence_after();
-      if (lane == 0) {
+      if (umma::elect_one()) {
         const uint32_t st = umma::smem_u32(smem + s * SM::STAGE_BYTES);
         const uint32_t a_hi = st, a_lo = st + OFF_ALO, b_hi = st + OFF_BHI, b_lo = st + OFF_BLO;
 #pragma unroll

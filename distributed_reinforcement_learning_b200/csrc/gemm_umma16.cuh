@@ -463,25 +463,25 @@ gemm_umma16_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, i
       const int s = t % STAGES;
       umma::mbar_wait(&full[s], (t / STAGES) & 1);
       umma::tc_fence_after();
-      if (lane == 0) {
+      if (umma::elect_one()) {
         TR(3000 + t);
         const uint32_t st = umma::smem_u32(smem + s * SM::STAGE_BYTES);
-        const uint32_t a_hi = st, a_lo = st + OFF_ALO, b_hi = st + OFF_BHI, b_lo = st + OFF_BLO;
+        // descriptors: constant part + (address >> 4); all offsets are multiples of 16 bytes
+        const uint64_t da_base = umma::make_desc(0, TA::LBO, TA::SBO, TA::LAYOUT_TYPE);
+        const uint64_t db_base = umma::make_desc(0, TB::LBO, TB::SBO, TB::LAYOUT_TYPE);
+        const uint64_t a_hi = umma::desc_at(da_base, st), a_lo = umma::desc_at(da_base, st + OFF_ALO);
+        const uint64_t b_hi = umma::desc_at(db_base, st + OFF_BHI), b_lo = umma::desc_at(db_base, st + OFF_BLO);
 #pragma unroll
         for (int j = 0; j < BK / 16; ++j) {
-          const uint32_t ao = TA::kslice_off(j), bo = TB::kslice_off(j);
-          const uint64_t dah = umma::make_desc(a_hi + ao, TA::LBO, TA::SBO, TA::LAYOUT_TYPE);
-          const uint64_t dbh = umma::make_desc(b_hi + bo, TB::LBO, TB::SBO, TB::LAYOUT_TYPE);
-          const uint64_t dbl = umma::make_desc(b_lo + bo, TB::LBO, TB::SBO, TB::LAYOUT_TYPE);
+          const uint64_t ao = (uint64_t)(TA::kslice_off(j) >> 4), bo = (uint64_t)(TB::kslice_off(j) >> 4);
           const uint32_t first = (t > 0 || j > 0) ? 1u : 0u;
           if (!AEX) {                                                    // small terms first
-            const uint64_t dal = umma::make_desc(a_lo + ao, TA::LBO, TA::SBO, TA::LAYOUT_TYPE);
-            umma16::mma_f16(tmem_base, dal, dbh, idesc, first);
-            umma16::mma_f16(tmem_base, dah, dbl, idesc, 1u);
+            umma16::mma_f16(tmem_base, a_lo + ao, b_hi + bo, idesc, first);
+            umma16::mma_f16(tmem_base, a_hi + ao, b_lo + bo, idesc, 1u);
           } else {
-            umma16::mma_f16(tmem_base, dah, dbl, idesc, first);
+            umma16::mma_f16(tmem_base, a_hi + ao, b_lo + bo, idesc, first);
           }
-          umma16::mma_f16(tmem_base, dah, dbh, idesc, 1u);
+          umma16::mma_f16(tmem_base, a_hi + ao, b_hi + bo, idesc, 1u);
         }
         umma::mma_commit(&empty[s]);
         if (t == ntiles - 1) umma::mma_commit(acc_full);

@@ -250,7 +250,7 @@ gemm_umma_persist_kernel(const AL al, const BL bl, const EP ep, int M, int N, in
         const uint32_t ph = (q / STAGES) & 1;
         umma::mbar_wait(&full[s], ph);
         umma::tc_fence_after();
-        if (lane == 0) {
+        if (umma::elect_one()) {
           const uint32_t st = umma::smem_u32(smem + s * SM::STAGE_BYTES);
           const uint32_t a_hi = st, a_lo = st + OFF_ALO, b_hi = st + OFF_BHI, b_lo = st + OFF_BLO;
 #pragma unroll

@@ -7,6 +7,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_umma.cuh"
 #include "gemm_umma16.cuh"
+#include "conv1_tma.cuh"
 #include "gemm_tma.cuh"
 #include "gemm_umma_persist.cuh"
 #include "kernels.h"
@@ -59,6 +60,8 @@ using X256L = Umma16Cfg<256, 2, 1, 8, 1, Fmt16, Fmt16>;      // lstm fwd: 96 KB 
 using X256W = Umma16Cfg<256, 2, 1, 8, 0, Fmt16, Fmt16>;      // lstm weight gradient
 using X128D = Umma16Cfg<128, 3, 1, 8, 1, Fmt16, Fmt16>;      // lstm data gradient: 64 KB per stage
 using X256D = Umma16Cfg<256, 2, 1, 8, 1, Fmt16, Fmt16>;      // dCol GEMMs (K = 64: one stage)
+using X64G = Umma16Cfg<64, 2, 2, 4, 0, Fmt16, Fmt16>;        // conv3 data gradient, gather form (K = 9 taps x 64)
+using X32G = Umma16Cfg<32, 3, 2, 4, 0, Fmt16, Fmt16>;        // conv2 data gradient, gather form (4 parity classes, K = 4 taps x 64)
 
 // math mode 3 (experimental): the persistent, fully warp-specialised variant of each tensor-core configuration
 template <class U> struct PersistOf;

@@ -4,6 +4,8 @@
 // Every dense contraction is one launch of a gather-GEMM: the FP32-FFMA core (gemm_simt.cuh, math
 // mode 1) or the tcgen05 3xTF32 tensor-core core (gemm_umma.cuh, math mode 2) -- same loaders and
 // epilogues.  The small head layers (M x 256 x 256) always use the FFMA core.
+#include <stdlib.h>
+
 #include "layer_defs.cuh"
 
 namespace drl {
@@ -129,7 +131,13 @@ int net_forward(const Streams& st, const ParamLayout& pl, const float* P, const 
     Conv1A al{in.frames, map};
     PlainB bl{P + pl.conv1_w, 32, 0};
     EpConv1 ep{act.a1, 32, P + pl.conv1_b, tma ? act.a1_lo : nullptr};
-    if (m16) {
+    // math mode 5: frame-resident TMA kernel (conv1_tma.cuh); DRL_B200_CONV1_GATHER=1 keeps the generic gather-GEMM
+    static const bool c1_gather = getenv("DRL_B200_CONV1_GATHER") != nullptr;
+    if (m16 && !c1_gather) {
+      prof_mark(s, "conv1_fwd");
+      DRL_TRY(launch_conv1_fwd_tma(s, in.frames, M, map, wi.img[0], ep));
+      ++n;
+    } else if (m16) {
       PretiledB<PlainB> blp{wi.img[0], 256 / 64};
       GEMM16("conv1_fwd", X32L, al, blp, ep, M * 400, 32, 256, 1, 256, 0);
     } else {
@@ -300,7 +308,15 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, const
     KERNEL("conv3_wgrad_reduce", splitk_reduce(s, bw.wg_part, slab, sp.splits, G + pl.conv3_w, slab), 1);
   }
   s = st.main;
-  if (mode >= 2) {
+  // DRL_B200_DGRAD_GATHER=1 (math mode 5): the data gradients of conv3 / conv2 as gather-GEMMs over the input pixels
+  // (K = taps x 64 output channels, ReLU mask in the epilogue) instead of dCol GEMM + col2im
+  static const bool dgrad_gather = getenv("DRL_B200_DGRAD_GATHER") != nullptr;
+  if (m16 && dgrad_gather) {
+    Conv3DA al{bw.da3};
+    Conv3DB bl{P + pl.conv3_w};
+    Conv3DE ep{bw.da2, act.a2};
+    GEMM16("conv3_dgrad", X64G, al, bl, ep, Mb * 81, 64, 576, 1, 576, 0);
+  } else if (mode >= 2) {
     // "dCol" form: one plain GEMM with K = 64 output channels (instead of gathering every dY value 9 times
     // through the producers), then a gather of <= 9 taps per input pixel with the ReLU mask.
     PlainA al{bw.da3, 64, 0};
@@ -335,7 +351,12 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, const
     KERNEL("conv2_wgrad_reduce", splitk_reduce(s, bw.wg_part, slab, sp.splits, G + pl.conv2_w, slab), 1);
   }
   s = st.main;
-  if (mode >= 2) {
+  if (m16 && dgrad_gather) {
+    Conv2DA al{bw.da2};
+    Conv2DB bl{P + pl.conv2_w};
+    Conv2DE ep{bw.da1, act.a1};
+    GEMM16("conv2_dgrad", X32G, al, bl, ep, Mb * 100, 32, 256, 4, 256, 0);
+  } else if (mode >= 2) {
     PlainA al{bw.da2, 64, 0};
     PlainBT bl{P + pl.conv2_w, 64, 0};               // B(k = co, n = (ky,kx,ci)) = W[n*64 + co]
     EpRaw<false> ep{bw.dcol, 512, 0, 1.0f, 0, 512};

@@ -383,10 +383,35 @@ struct EpBiasAct {
       else lo[off] = tf32_rem(o[0]);
     }
   }
+  // hoisted-bias form used by the tensor-core epilogues (epilogue_store_32x32)
+  __device__ __forceinline__ float4 bias4(int z, int n) const {
+    return BIAS ? __ldg(reinterpret_cast<const float4*>(bias + z * sbias + n)) : zero4();
+  }
+  __device__ __forceinline__ void store4b(int z, int m, int n, const float (&v)[4], const float4& b) const {
+    const float bb[4] = {b.x, b.y, b.z, b.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float t = v[j] * scale + bb[j];
+      o[j] = RELU ? fmaxf(t, 0.f) : t;
+    }
+    const size_t off = z * sz + (size_t)m * ldc + n;
+    *reinterpret_cast<float4*>(c + off) = make_float4(o[0], o[1], o[2], o[3]);
+    if (lo) *reinterpret_cast<float4*>(lo + off) = make_float4(tf32_rem(o[0]), tf32_rem(o[1]), tf32_rem(o[2]), tf32_rem(o[3]));
+  }
   __device__ __forceinline__ void store_colsum(int, int, float) const {}
 };
+// x / 255 without the IEEE-division subroutine: nvcc turns `x / 255.0f` into FCHK + a CALL to its slow-path routine that
+// cost ~250 cycles per element here (tools/conv1_timeline.py: 32 divisions per thread made the epilogue of a 128x32 tile
+// take 11,000 cycles, 80 % of the conv1 kernel).  q = x*r, one FMA residual step: the correctly rounded quotient for all
+// finite x outside the denormal range (r = RN(1/255); the residual is exact in FMA arithmetic).
+__device__ __forceinline__ float div255(float x) {
+  const float r = 1.0f / 255.0f;
+  const float q = x * r;
+  return fmaf(fmaf(-q, 255.0f, x), r, q);
+}
 // conv1: the frame bytes are kept as exact integers in the contraction and the /255 of
-// agent/impala.py:133 is applied to the accumulator (true fp32 divide), then bias + ReLU.
+// agent/impala.py:133 is applied to the accumulator (correctly rounded fp32 quotient, div255), then bias + ReLU.
 struct EpConv1 {
   static constexpr bool kColSum = false;
   float* c; int ldc;
@@ -396,7 +421,7 @@ struct EpConv1 {
   __device__ __forceinline__ void store(int, int m, int n, const float (&v)[V]) const {
     float o[V];
 #pragma unroll
-    for (int j = 0; j < V; ++j) o[j] = fmaxf(v[j] / 255.0f + __ldg(bias + n + j), 0.f);
+    for (int j = 0; j < V; ++j) o[j] = fmaxf(div255(v[j]) + __ldg(bias + n + j), 0.f);
     const size_t off = (size_t)m * ldc + n;
     if constexpr (V == 4) *reinterpret_cast<float4*>(c + off) = make_float4(o[0], o[1], o[2], o[3]);
     else c[off] = o[0];
@@ -405,6 +430,16 @@ struct EpConv1 {
         *reinterpret_cast<float4*>(lo + off) = make_float4(tf32_rem(o[0]), tf32_rem(o[1]), tf32_rem(o[2]), tf32_rem(o[3]));
       else lo[off] = tf32_rem(o[0]);
     }
+  }
+  __device__ __forceinline__ float4 bias4(int, int n) const { return __ldg(reinterpret_cast<const float4*>(bias + n)); }
+  __device__ __forceinline__ void store4b(int, int m, int n, const float (&v)[4], const float4& b) const {
+    const float bb[4] = {b.x, b.y, b.z, b.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = fmaxf(div255(v[j]) + bb[j], 0.f);
+    const size_t off = (size_t)m * ldc + n;
+    *reinterpret_cast<float4*>(c + off) = make_float4(o[0], o[1], o[2], o[3]);
+    if (lo) *reinterpret_cast<float4*>(lo + off) = make_float4(tf32_rem(o[0]), tf32_rem(o[1]), tf32_rem(o[2]), tf32_rem(o[3]));
   }
   __device__ __forceinline__ void store_colsum(int, int, float) const {}
 };

@@ -2,7 +2,9 @@
 //   lr    = polynomial_decay(start, global_step, decay_steps, end)  (power 1, evaluated in float32)
 //   g    <- g * clip * min(1/||g||_2, 1/clip)                        (tf.clip_by_global_norm over ALL params)
 //   ms   <- ms + (1 - 0.99) (g^2 - ms)     (RMSProp slot initialised to ONES)
-//   w    <- w - lr * g / sqrt(ms + 0.1)     (epsilon INSIDE the sqrt, momentum 0, not centred)
+//   w    <- w - lr * g / sqrt(ms + 0.1)     (epsilon INSIDE the sqrt, momentum 0, not centred; evaluated as
+//           lr * g * rsqrt(ms + 0.1) like TF's Eigen kernel -- rsqrt.approx is within 2 ulp and avoids the IEEE-division
+//           subroutine, which made this HBM-bound kernel ALU-bound)
 //   global_step += 1
 // Two launches over the flat padded vectors: (1) partial sums of squares (+ lr, step), (2) every
 // block re-reduces the partials in a fixed order (deterministic) and applies the update.
@@ -86,10 +88,10 @@ __global__ void __launch_bounds__(256) rmsprop_apply_kernel(OptState o) {
     const float4 g = g4[i];
     float4 m = m4[i], w = w4[i];
     float gg;
-    gg = g.x * scale; m.x += (gg * gg - m.x) * (1.0f - 0.99f); w.x -= lr * gg / sqrtf(m.x + 0.1f);
-    gg = g.y * scale; m.y += (gg * gg - m.y) * (1.0f - 0.99f); w.y -= lr * gg / sqrtf(m.y + 0.1f);
-    gg = g.z * scale; m.z += (gg * gg - m.z) * (1.0f - 0.99f); w.z -= lr * gg / sqrtf(m.z + 0.1f);
-    gg = g.w * scale; m.w += (gg * gg - m.w) * (1.0f - 0.99f); w.w -= lr * gg / sqrtf(m.w + 0.1f);
+    gg = g.x * scale; m.x += (gg * gg - m.x) * (1.0f - 0.99f); w.x -= lr * gg * rsqrtf(m.x + 0.1f);
+    gg = g.y * scale; m.y += (gg * gg - m.y) * (1.0f - 0.99f); w.y -= lr * gg * rsqrtf(m.y + 0.1f);
+    gg = g.z * scale; m.z += (gg * gg - m.z) * (1.0f - 0.99f); w.z -= lr * gg * rsqrtf(m.z + 0.1f);
+    gg = g.w * scale; m.w += (gg * gg - m.w) * (1.0f - 0.99f); w.w -= lr * gg * rsqrtf(m.w + 0.1f);
     m4[i] = m; w4[i] = w;
   }
 }
