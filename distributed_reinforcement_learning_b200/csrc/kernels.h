@@ -119,6 +119,8 @@ struct Streams {
   cudaStream_t main, side;
   cudaEvent_t ev[8];
   bool par;
+  cudaEvent_t ev_lstm_grads = nullptr;   // backward: recorded on the side stream once the head and LSTM weight gradients
+                                         // are in the bucket (the early part of the peer exchange waits for it)
 };
 // mode: 1 = FP32-FFMA gather-GEMM, 2 = tcgen05 3xTF32 gather-GEMM for the large contractions
 int net_forward(const Streams& st, const ParamLayout& pl, const float* params, const WeightImages& wi, const Inputs& in,
@@ -194,7 +196,9 @@ int adam_step(cudaStream_t s, const AdamState& o);   // 2 launches: partial norm
 
 // ---- peer.cu: gradient exchange over NVLink peer memory (CUDA IPC), fused with the norm ------------------------
 constexpr int kMaxPeers = 16;
-constexpr int kPeerParts = 1;      // exchange instances per step (the kernel takes a sub-range: see DESIGN.md section 5)
+constexpr int kPeerParts = 2;      // exchange instances per step: part 0 = [lstm .. end) of the bucket (96 % of the bytes, complete when
+                                   // the LSTM weight gradient is, ~230 us before the backward pass ends) on its own stream with a small
+                                   // grid; part 1 = [conv1 .. emb2] after the backward pass
 struct PeerTable {                 // device pointers into every rank's buffers (index = rank; own entries are local)
   float* bucket[kMaxPeers];        // [padded grads | 4 loss sums]
   float* reduced[kMaxPeers];       // same shape: the summed bucket, delivered by the owners of the slices
@@ -211,6 +215,6 @@ struct PeerPlan {
   int rank, world, nblk;
 };
 // one exchange instance over float4 range [beg4, end4) of the bucket; do_lr: also lr / global_step (last instance)
-int peer_exchange(cudaStream_t s, const PeerPlan& pp, int part, int64_t beg4, int64_t end4, bool do_lr);
+int peer_exchange(cudaStream_t s, const PeerPlan& pp, int part, int64_t beg4, int64_t end4, bool do_lr, int grid = 0);
 
 }  // namespace drl

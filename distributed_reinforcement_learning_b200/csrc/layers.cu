@@ -280,6 +280,8 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, const
     EpRaw<true> ep{G + pl.lstm_w, Geo::G4, 0, 1.0f, Geo::XK, Geo::G4};
     if (m16) GEMM16("lstm_wgrad", X256W, al, bl, ep, Geo::XK, Geo::G4, Mb, 1, Mb, 0);
     else GEMM("lstm_wgrad", CfgBig, U256, al, bl, ep, Geo::XK, Geo::G4, Mb, 1, Mb, 0);   // 29 x 4 = 116 CTAs: one wave
+    // the head gradients (earlier on this stream) and the LSTM gradient are now in the bucket: [lstm_w .. end)
+    if (st.par && st.ev_lstm_grads) DRL_CUDA_CHECK(cudaEventRecord(st.ev_lstm_grads, side));
   }
   s = st.main;
   {  // d[a3 | emb] = dz W[:3392]^T  (h0, c0 are fed data: no gradient, agent/impala.py:38-39)

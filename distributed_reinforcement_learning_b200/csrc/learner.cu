@@ -122,7 +122,9 @@ struct drl_learner {
   drl_learner_config cfg{};
   int B = 0, T = 0, A = 0, M = 0, Mb = 0, mode = 1;
   ParamLayout pl{};
-  cudaStream_t compute = nullptr, copy = nullptr, side = nullptr;
+  cudaStream_t compute = nullptr, copy = nullptr, side = nullptr, xchg = nullptr;
+  cudaEvent_t ev_lstm_grads = nullptr, ev_xchg_done = nullptr;   // early part of the peer exchange (stream xchg)
+  int peer_early_ctas = 64;   // grid of the early exchange instance (DRL_B200_PEER_EARLY_CTAS; 0 = no early part)
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done = nullptr;
   cudaEvent_t fj[8] = {};    // fork/join events between the compute and the side stream
   bool par = true;           // run off-critical-path kernels on the side stream
@@ -226,6 +228,7 @@ Streams streams_of(const drl_learner* h) {
   st.side = h->side;
   for (int i = 0; i < 8; ++i) st.ev[i] = h->fj[i];
   st.par = h->par;
+  st.ev_lstm_grads = (h->peer_on && h->peer_early_ctas > 0) ? h->ev_lstm_grads : nullptr;
   return st;
 }
 
@@ -256,7 +259,8 @@ int enqueue_forward_backward(drl_learner* h, int slot) {
 }
 
 // local_only: the single-replica update on the local bucket even when the peer exchange is on (profiling on one rank)
-int enqueue_apply(drl_learner* h, int out_row, bool local_only = false) {
+// early: the backward pass of THIS enqueue recorded ev_lstm_grads (one-graph step): part 0 of the exchange overlaps it
+int enqueue_apply(drl_learner* h, int out_row, bool local_only = false, bool early = false) {
   pdl_break(h->compute);
   OptState o_local = h->opt, o_peer = h->plan.o;
   o_local.out = o_peer.out = h->d_out + 8 * out_row;
@@ -264,7 +268,19 @@ int enqueue_apply(drl_learner* h, int out_row, bool local_only = false) {
     prof_mark(h->compute, "peer_exchange");
     {
       NvtxRange r("drl:exchange");
-      DRL_TRY(peer_exchange(h->compute, h->plan, 0, 0, h->pl.padded_total / 4 + 1, true));   // grads + loss sums
+      // part 0: [lstm_w .. end) incl. the loss sums -- 96 % of the bucket.  In the one-graph step it runs on its own stream
+      // behind the LSTM weight gradient (ev_lstm_grads), i.e. under the rest of the backward pass, with a small grid so that
+      // the convolution kernels never queue behind it; otherwise right here.  part 1: [0 .. lstm_w), after the backward pass.
+      const int64_t split4 = h->pl.lstm_w / 4, end4 = h->pl.padded_total / 4 + 1;
+      if (early) {
+        DRL_CUDA_CHECK(cudaStreamWaitEvent(h->xchg, h->ev_lstm_grads, 0));
+        DRL_TRY(peer_exchange(h->xchg, h->plan, 0, split4, end4, false, h->peer_early_ctas));
+        DRL_CUDA_CHECK(cudaEventRecord(h->ev_xchg_done, h->xchg));
+        DRL_CUDA_CHECK(cudaStreamWaitEvent(h->compute, h->ev_xchg_done, 0));
+      } else {
+        DRL_TRY(peer_exchange(h->compute, h->plan, 0, split4, end4, false, h->peer_early_ctas));
+      }
+      DRL_TRY(peer_exchange(h->compute, h->plan, 1, 0, split4, true, 148));
     }
     prof_mark(h->compute, "optimizer(rmsprop)");
     NvtxRange r("drl:update");
@@ -346,7 +362,7 @@ int run_step(drl_learner* h, int slot) {
       cudaGraph_t g = nullptr;
       DRL_CUDA_CHECK(cudaStreamBeginCapture(h->compute, cudaStreamCaptureModeThreadLocal));
       int r = enqueue_forward_backward(h, slot);
-      if (r == DRL_OK) r = enqueue_apply(h, slot);
+      if (r == DRL_OK) r = enqueue_apply(h, slot, false, h->peer_on && h->par && h->peer_early_ctas > 0);
       cudaError_t e = cudaStreamEndCapture(h->compute, &g);
       if (r != DRL_OK) { if (g) cudaGraphDestroy(g); return r; }
       if (e != cudaSuccess) { set_error("graph capture failed: %s", cudaGetErrorString(e)); return DRL_ERR_CUDA; }
@@ -357,7 +373,7 @@ int run_step(drl_learner* h, int slot) {
     DRL_CUDA_CHECK(cudaGraphLaunch(h->graph_step[slot], h->compute));
   } else {
     DRL_TRY(enqueue_forward_backward(h, slot));
-    DRL_TRY(enqueue_apply(h, slot));
+    DRL_TRY(enqueue_apply(h, slot, false, h->peer_on && h->par && h->peer_early_ctas > 0));
   }
   h->last_out = slot;
   DRL_CUDA_CHECK(cudaEventRecord(sl.consumed, h->compute));
@@ -427,6 +443,10 @@ int drl_learner_create(const drl_learner_config* cfg, drl_learner** out) {
     DRL_CUDA_CHECK(cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
     DRL_CUDA_CHECK(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
     DRL_CUDA_CHECK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    DRL_CUDA_CHECK(cudaStreamCreateWithFlags(&h->xchg, cudaStreamNonBlocking));
+    DRL_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_lstm_grads, cudaEventDisableTiming));
+    DRL_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_xchg_done, cudaEventDisableTiming));
+    if (const char* e = getenv("DRL_B200_PEER_EARLY_CTAS")) h->peer_early_ctas = atoi(e);
     for (int i = 0; i < 8; ++i) DRL_CUDA_CHECK(cudaEventCreateWithFlags(&h->fj[i], cudaEventDisableTiming));
     DRL_CUDA_CHECK(cudaEventCreate(&h->ev_start));
     DRL_CUDA_CHECK(cudaEventCreate(&h->ev_stop));
@@ -571,6 +591,9 @@ int drl_learner_destroy(drl_learner* h) {
   for (auto e : h->ev_done_slot) if (e) cudaEventDestroy(e);
   for (int i = 0; i < 8; ++i) if (h->fj[i]) cudaEventDestroy(h->fj[i]);
   if (h->side) cudaStreamDestroy(h->side);
+  if (h->xchg) cudaStreamDestroy(h->xchg);
+  if (h->ev_lstm_grads) cudaEventDestroy(h->ev_lstm_grads);
+  if (h->ev_xchg_done) cudaEventDestroy(h->ev_xchg_done);
   if (h->compute) cudaStreamDestroy(h->compute);
   if (h->copy) cudaStreamDestroy(h->copy);
   cudaGetLastError();

@@ -122,8 +122,11 @@ __global__ void __launch_bounds__(kPeerThreads) peer_reduce_kernel(PeerTable t, 
 }
 
 // one exchange instance; the update kernel waits for every instance's "delivered" flags in its prologue
-int peer_exchange(cudaStream_t s, const PeerPlan& pp, int part, int64_t beg4, int64_t end4, bool do_lr) {
-  DRL_CUDA_CHECK((launch_k(peer_reduce_kernel, pp.nblk, kPeerThreads, 0, s, pp.t, pp.o, pp.rank, pp.world, pp.nblk, part, beg4, end4,
+int peer_exchange(cudaStream_t s, const PeerPlan& pp, int part, int64_t beg4, int64_t end4, bool do_lr, int grid) {
+  // grid <= pp.nblk: the partial-norm table has pp.nblk entries per (part, rank); a smaller grid leaves the rest at their
+  // initial zeros (the grid of a part never changes during the handle's life)
+  if (grid <= 0 || grid > pp.nblk) grid = pp.nblk;
+  DRL_CUDA_CHECK((launch_k(peer_reduce_kernel, grid, kPeerThreads, 0, s, pp.t, pp.o, pp.rank, pp.world, pp.nblk, part, beg4, end4,
                            do_lr ? 1 : 0)));
   return DRL_OK;
 }

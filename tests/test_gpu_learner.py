@@ -166,7 +166,10 @@ def test_data_parallel_shards_sum_to_full_batch(native):
     assert parity.rel_err(g_sum, g_full) < parity.TOL
     L = it.Learner(params, torch.float64, "dedup", **cfg)
     _, g = L.gradients(*[batch[k] for k in fields])
-    assert parity.rel_err(g_sum, it.flatten_grads(g)) < parity.TOL
+    # against the UNMASKED float64 oracle over the whole flat vector: one ReLU pre-activation within float32 rounding of
+    # zero flips the mask and moves that image's conv gradients by O(1e-3) (tests/parity.py; compare_step evaluates the
+    # oracle at the GPU's activation pattern and holds 1e-4) -- here the looser kink bar applies
+    assert parity.rel_err(g_sum, it.flatten_grads(g)) < 2e-3
 
 
 def test_errors_are_loud(native):
