@@ -215,6 +215,12 @@ NCU_TRAFFIC_B32 = {"lstm_fwd": 38.70e6, "lstm_wgrad": 10.25e6, "lstm_dgrad": 37.
                    "conv3_wgrad": 19.22e6, "conv2_dgrad": 49.42e6, "conv3_dgrad": 16.57e6}
 
 
+# the same for the split-16 kernels (math mode 5), from profiles/r02_ncu_umma16_full.md
+NCU_TRAFFIC_B32_M5 = {"conv2_fwd": 32.95e6, "conv3_fwd": 13.47e6, "lstm_fwd": 23.68e6, "lstm_wgrad": 10.24e6,
+                      "lstm_dgrad": 23.78e6, "conv3_wgrad": 19.21e6, "conv3_dgrad": 16.60e6, "conv2_wgrad": 41.74e6,
+                      "conv2_dgrad": 50.96e6}
+
+
 def step_flops(B):
     M, Mb = B * T, B * (T - 2)
     return 2.0 * 11810048 * M + 2.0 * 2.0 * 11810048 * Mb       # SURVEY.md App. B (upper bound incl. conv1 dgrad)
@@ -430,8 +436,10 @@ def run_ours(args):
                 # fp32-grade results cost 3 tf32 MMAs per product and tf32 runs at half the bf16 rate:
                 "frac_of_3xtf32_ceiling": ach / (peaks["tf_sus"] / 6.0) if args.math_mode in (2, 3, 4) else None,
                 "frac_of_3x16bit_ceiling": ach / (peaks["tf_sus"] / 3.0) if args.math_mode == 5 else None,
-                "traffic": NCU_TRAFFIC_B32.get(name) if (args.math_mode == 2 and B == 32) else None,
-                "traffic_source": "profiles/r01_ncu_umma_full.md (ncu --set full, per launch)",
+                "traffic": (NCU_TRAFFIC_B32.get(name) if args.math_mode == 2 else
+                            NCU_TRAFFIC_B32_M5.get(name) if args.math_mode == 5 else None) if B == 32 else None,
+                "traffic_source": ("profiles/r02_ncu_umma16_full.md" if args.math_mode == 5 else
+                                   "profiles/r01_ncu_umma_full.md") + " (ncu --set full, dram read + write per launch)",
                 "peak_source": peaks["src"] + " bf16 sustained",
                 "math_mode": MATH_MODES[args.math_mode] + "; achieved = algorithmic 2MNK flops (counted once, "
                              "not x3) / CUDA-event time",
@@ -489,8 +497,8 @@ def run_ours(args):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of vtrace_from_softmax_pipe_kernel at [65536,18,18], from the
-# ncu --set full capture summarised in profiles/ (None until captured)
-NCU_TRAFFIC_VTRACE = None
+# ncu --set full capture summarised in profiles/r02_ncu_vtrace.md
+NCU_TRAFFIC_VTRACE = 201.4e6
 
 
 def vtrace_roofline(torch, peaks, Bv=65536, Tv=18, reps=20):

@@ -59,7 +59,8 @@ using X64W = Umma16Cfg<64, 2, 2, 4, 0, Fmt16, Fmt16>;        // conv2 / conv3 we
 using X256L = Umma16Cfg<256, 2, 1, 8, 1, Fmt16, Fmt16>;      // lstm fwd: 96 KB per stage
 using X256W = Umma16Cfg<256, 2, 1, 8, 0, Fmt16, Fmt16>;      // lstm weight gradient
 using X128D = Umma16Cfg<128, 3, 1, 8, 1, Fmt16, Fmt16>;      // lstm data gradient: 64 KB per stage
-using X256D = Umma16Cfg<256, 2, 1, 8, 1, Fmt16, Fmt16>;      // dCol GEMMs (K = 64: one stage)
+using X256D = Umma16Cfg<256, 1, 2, 8, 1, Fmt16, Fmt16>;      // dCol GEMMs (K = 64 = ONE stage of 96 KB): two CTAs per SM, so that
+                                                             // the 128 KB epilogue of one overlaps the load + MMAs of the other
 using X64G = Umma16Cfg<64, 2, 2, 4, 0, Fmt16, Fmt16>;        // conv3 data gradient, gather form (K = 9 taps x 64)
 using X32G = Umma16Cfg<32, 3, 2, 4, 0, Fmt16, Fmt16>;        // conv2 data gradient, gather form (4 parity classes, K = 4 taps x 64)
 

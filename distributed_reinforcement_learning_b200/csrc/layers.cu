@@ -376,7 +376,16 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, const
     GEMM_FFMA("conv2_dgrad", CfgN32, al, bl, ep, Mb * 100, 32, 256, 4, 256, 0);
   }
   // ---- conv1 (input is data: weight gradient only) -----------------------------------------
-  {
+  static const bool c1w_gather = getenv("DRL_B200_CONV1_GATHER") != nullptr;
+  if (m16 && !c1w_gather) {
+    // frame-resident TMA kernel (conv1_tma.cuh): one partial slab per CTA, then the fixed-order reduce
+    const size_t slab = 257 * 32;
+    int splits = 0;
+    prof_mark(s, "conv1_wgrad");
+    DRL_TRY(launch_conv1_wgrad_tma(s, in.frames, M, Mb, map, bw.da1, bw.wg_part2, bw.wg_part_floats, &splits));
+    ++n;
+    KERNEL("conv1_wgrad_reduce", splitk_reduce(s, bw.wg_part2, slab, splits, G + pl.conv1_w, slab), 1);
+  } else {
     const SplitPlan sp = plan_conv1_wgrad(Mb, mode);
     const size_t slab = 257 * 32;
     Conv1WA al{in.frames, map};
