@@ -53,7 +53,10 @@ __device__ __forceinline__ bool wait_peers(const uint32_t* my_flags, int phase, 
     }
   }
   __syncthreads();
-  return ok_s != 0;
+  const bool ok = ok_s != 0;
+  __syncthreads();   // a kernel may call wait_peers again (one call per exchange part): everyone has read ok_s before
+                     // thread 0 of the next call overwrites it (racecheck, 2 GPUs: profiles/r02_sanitizer_peer_racecheck*.log)
+  return ok;
 }
 
 

@@ -1,4 +1,5 @@
-"""PyTorch-CPU restatement of the reference A3C learner step -- TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED (TensorFlow
+"""PyTorch-CPU restatement of the reference A3C learner step -- TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED for this
+family (outside SURVEY.md section 8: the executed-reference pin of ``oracle/ref_exec.py`` covers IMPALA, Ape-X and R2D2; TensorFlow
 1.14 is not installable, the reference ships no tests); float64 = truth, float32 = CPU baseline.
 
 Follows:

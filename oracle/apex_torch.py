@@ -1,8 +1,10 @@
 """PyTorch-CPU restatement of the reference Ape-X DQN learner step -- TEST INFRASTRUCTURE ONLY.
 
 float64 instance = truth for tolerances; float32 instance = "CPU restatement of the reference, not
-TF1" timing baseline.  PARITY UNPINNED (see ``oracle/__init__.py``): TensorFlow 1.14 is not
-installable here and the reference ships no tests; the TF kernel semantics (conv2d VALID/NHWC/HWIO,
+TF1" timing baseline.  PINNED (see ``oracle/__init__.py``): ``tests/test_oracle_refexec.py`` executes the unmodified
+``agent/apex.py`` / ``model/apex_value.py`` over ``oracle/tf1_shim`` and this restatement equals it (q values, loss, |td|,
+Adam steps, target sync) in float64.  TensorFlow 1.14 itself is not
+installable here; the TF OP-KERNEL semantics (conv2d VALID/NHWC/HWIO,
 AdamOptimizer's ApplyAdam, clip_by_global_norm with ``None`` gradients skipped, polynomial_decay in
 float32, tf.argmax = first maximal index) are restated from the TF 1.14 documentation.
 

@@ -1,8 +1,10 @@
 """PyTorch-CPU restatement of the reference IMPALA learner step -- TEST INFRASTRUCTURE ONLY.
 
 float64 instance = truth for tolerances; float32 instance = "CPU restatement of the
-reference, not TF1" timing baseline.  PARITY UNPINNED (see ``oracle/__init__.py``): the
-TensorFlow 1.14 kernel semantics used here (conv2d VALID/NHWC/HWIO cross-correlation,
+reference, not TF1" timing baseline.  PINNED (see ``oracle/__init__.py``): ``tests/test_oracle_refexec.py`` executes the
+unmodified ``agent/impala.py`` / ``model/impala_actor_critic.py`` over ``oracle/tf1_shim`` and this restatement equals it
+(taps, losses, all gradients, three RMSProp steps) to ~1e-12 in float64.  The
+TensorFlow 1.14 OP-KERNEL semantics shared by shim and restatement (conv2d VALID/NHWC/HWIO cross-correlation,
 LSTMCell gate order i,j,f,o with forget_bias 1.0, RMSProp ms0=1 / eps inside sqrt,
 clip_by_global_norm, polynomial_decay) are restated from SURVEY.md Appendix A.
 

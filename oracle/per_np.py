@@ -6,8 +6,10 @@ of total/n, importance weights (n_entries * p/total) ** -beta normalised by thei
 0.001 per ``sample`` call.  The uniform draw of ``random.uniform(a, b)`` is taken as a + (b - a) * u with u supplied
 by the caller, which is what CPython's ``random.uniform`` computes from ``random.random()``.
 
-PARITY UNPINNED like the rest of the oracle (the reference ships no tests); pinned here by hand-computed totals and
-by the invariants (every internal node = sum of its children, sampled leaf contains the drawn mass).
+PINNED: the reference's ``SumTree`` / ``Memory`` are plain NumPy, so ``tests/test_oracle_refexec.py`` executes them as
+they are (CPython ``random`` seeded) and this restatement equals them bit for bit (tree nodes, sampled indices, weights,
+beta); further pinned by hand-computed totals and the invariants (every internal node = sum of its children, the
+sampled leaf contains the drawn mass).
 """
 import numpy as np
 

@@ -1,8 +1,9 @@
 """PyTorch-CPU restatement of the reference R2D2 learner step -- TEST INFRASTRUCTURE ONLY.
 
 float64 instance = truth for tolerances; float32 instance = "CPU restatement of the reference, not TF1" timing
-baseline.  PARITY UNPINNED (see ``oracle/__init__.py``): TensorFlow 1.14 is not installable here and the reference
-ships no tests; TF kernel semantics (LSTMCell gate order i,j,f,o with forget_bias 1.0, dynamic_rnn over a
+baseline.  PINNED (see ``oracle/__init__.py``): ``tests/test_oracle_refexec.py`` executes the unmodified ``agent/r2d2.py`` /
+``model/r2d2_lstm.py`` / ``optimizer/burn_in.py`` over ``oracle/tf1_shim`` and this restatement equals it in float64.  TensorFlow 1.14
+itself is not installable here; TF OP-KERNEL semantics (LSTMCell gate order i,j,f,o with forget_bias 1.0, dynamic_rnn over a
 length-1 sequence from a fed (c, h) state, AdamOptimizer.minimize = ApplyAdam without clipping) restated from
 the TF 1.14 documentation.
 

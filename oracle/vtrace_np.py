@@ -2,7 +2,8 @@
 
 Every function keeps the reference's name, argument order and layout and cites the lines it
 follows.  The dtype of the computation is the dtype of the inputs (float64 for the truth
-oracle, float32 to mimic the TF1 CPU kernels).  PARITY UNPINNED -- see ``oracle/__init__.py``.
+oracle, float32 to mimic the TF1 CPU kernels).  PINNED: ``tests/test_oracle_refexec.py`` executes the unmodified
+``optimizer/vtrace.py`` over ``oracle/tf1_shim`` and every function here equals it to ~1e-12 (see ``oracle/__init__.py``).
 """
 import numpy as np
 

@@ -345,3 +345,55 @@ def test_r2d2_executed_reference_equals_restatement():
     L.main_to_target()
     for n in R.var:
         assert np.array_equal(R.target_params()[n], R.params()[n])
+
+
+# ---- distributed_queue/buffer_queue.py:326-415 SumTree / Memory: plain NumPy in the reference -> executed as is -----
+def test_reference_sumtree_and_memory_executed_equal_restatement_and_native():
+    """The reference's prioritized replay memory has no TF in it: its own ``SumTree`` / ``Memory`` classes are executed
+    (CPython ``random`` seeded) against ``oracle.per_np`` and -- when the library is built -- the ``drl_per_*`` mirror,
+    over a wrap-around fill, interleaved priority updates and 40 ``sample`` calls: tree nodes, sampled tree indices,
+    data and the beta schedule bit for bit, importance weights bit for bit (NumPy) / to 1 ulp (libm ``pow`` in csrc/per.cu)."""
+    import random
+
+    from oracle import per_np
+    ref = ref_exec.load(("distributed_queue.buffer_queue",), float_dtype=torch.float64)
+    RMem = ref["distributed_queue.buffer_queue"].Memory
+    cap, n = 37, 8
+    rmem, omem = RMem(cap), per_np.MemoryNP(cap)
+    try:
+        from distributed_reinforcement_learning_b200.distributed_queue import buffer_queue
+        nmem = buffer_queue.Memory(cap)
+    except Exception:
+        nmem = None
+    rng = np.random.default_rng(11)
+    for i in range(cap + 9):                            # wraps: the 9 oldest records are overwritten
+        e = float(abs(rng.standard_normal()) * 3)
+        rmem.add(e, ("rec", i))
+        omem.add(e)
+        if nmem is not None:
+            nmem.add(e, ("rec", i))
+    np.testing.assert_array_equal(rmem.tree.tree, omem.tree.nodes)
+    assert rmem.tree.n_entries == omem.tree.n_entries == cap and rmem.tree.write == 9
+    for it_ in range(40):
+        random.seed(1000 + it_)
+        rbatch, ridx, rw = rmem.sample(n)
+        random.seed(1000 + it_)
+        u = [random.random() for _ in range(n)]
+        oidx, odata, oprio, ow = omem.sample(n, u)
+        assert list(oidx) == ridx and rmem.beta == omem.beta == pytest.approx(min(1.0, 0.4 + 0.001 * (it_ + 1)), abs=1e-15)
+        np.testing.assert_array_equal(ow, rw)
+        assert [rmem.tree.data[j] for j in odata] == rbatch
+        if nmem is not None:
+            nbatch, nidx, nw = nmem.sample(n, u)
+            assert nidx == ridx and nbatch == rbatch and nmem.beta == rmem.beta
+            np.testing.assert_allclose(nw, rw, rtol=4e-16, atol=0)   # libm pow vs NumPy's SIMD pow: <= 1 ulp
+        for j in ridx[::2]:                             # the learner writes new |td| back (train_apex.py:121-124)
+            e = float(abs(rng.standard_normal()))
+            rmem.update(j, e)
+            omem.update(j, e)
+            if nmem is not None:
+                nmem.update(j, e)
+        np.testing.assert_allclose(rmem.tree.tree, omem.tree.nodes, rtol=0, atol=0)
+        assert rmem.tree.total() == omem.tree.total()
+        if nmem is not None:
+            assert nmem.tree.total() == rmem.tree.total()
