@@ -55,6 +55,7 @@ using Fmt16 = umma16::BF16;     // every GEMM whose operands are fp32 activation
 using FmtC1 = umma16::F16;      // conv1: uint8 frames (exact) x weights
 using X32L = Umma16Cfg<32, 4, 2, 4, 1, FmtC1, FmtC1>;        // conv1 fwd: whole K = 256 resident
 using X64L = Umma16Cfg<64, 2, 2, 4, 1, Fmt16, Fmt16>;        // conv2 / conv3 fwd: 48 KB per K = 64 stage, 2 CTAs per SM
+using X64L8 = Umma16Cfg<64, 4, 1, 8, 1, Fmt16, Fmt16>;       // experiment (DRL_B200_C2F=1): one CTA per SM, 8 producer warps, 4 stages
 using X64W = Umma16Cfg<64, 2, 2, 4, 0, Fmt16, Fmt16>;        // conv2 / conv3 weight gradients (both operands gathered)
 using X256L = Umma16Cfg<256, 2, 1, 8, 1, Fmt16, Fmt16>;      // lstm fwd: 96 KB per stage
 using X256W = Umma16Cfg<256, 2, 1, 8, 0, Fmt16, Fmt16>;      // lstm weight gradient

@@ -157,7 +157,9 @@ int net_forward(const Streams& st, const ParamLayout& pl, const float* P, const 
     PlainB bl{P + pl.conv2_w, 64, 0};
     PretiledB<PlainB> blp{wi.img[1], m16 ? 512 / 64 : 512 / 32};
     EpBiasAct<true, true> ep{act.a2, 64, 0, P + pl.conv2_b, 0, 1.0f};
-    if (m16) GEMM16("conv2_fwd", X64L, al, blp, ep, M * 81, 64, 512, 1, 512, 0);
+    static const int c2f = getenv("DRL_B200_C2F") ? atoi(getenv("DRL_B200_C2F")) : 0;
+    if (m16 && c2f == 1) GEMM16("conv2_fwd", X64L8, al, blp, ep, M * 81, 64, 512, 1, 512, 0);
+    else if (m16) GEMM16("conv2_fwd", X64L, al, blp, ep, M * 81, 64, 512, 1, 512, 0);
     else GEMM_W("conv2_fwd", CfgBig, U64L, al, bl, blp, ep, M * 81, 64, 512, 1, 512, 0);
   }
   // conv3 -> a3 [M,7,7,64] = flatten HWC [M,3136]   (:8-10)
