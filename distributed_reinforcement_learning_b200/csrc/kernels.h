@@ -119,6 +119,11 @@ struct Streams {
   cudaStream_t main, side;
   cudaEvent_t ev[8];
   bool par;
+  // optional second side lane (IMPALA handle): the four small, latency-bound head weight gradients run here so that they
+  // do not sit in front of lstm_wgrad / the conv weight gradients on `side` (tools/timeline.py: the serial side stream
+  // ended 35 us after the main chain).  nullptr: everything stays on `side`.
+  cudaStream_t side2 = nullptr;
+  cudaEvent_t ev2[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_lstm_grads = nullptr;   // backward: recorded on the side stream once the head and LSTM weight gradients
                                          // are in the bucket (the early part of the peer exchange waits for it)
 };

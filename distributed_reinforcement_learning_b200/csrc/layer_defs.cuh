@@ -158,6 +158,21 @@ static inline int fork_to_side(const Streams& st, int i) {
   pdl_break(st.side);   // the next side-stream kernel depends on a kernel of another stream: full dependency
   return DRL_OK;
 }
+// main -> side2 edge (ev2[i]); side2 -> other stream edge
+static inline int fork_to_side2(const Streams& st, int i) {
+  if (!st.par || !st.side2) return DRL_OK;
+  DRL_CUDA_CHECK(cudaEventRecord(st.ev2[i], st.main));
+  DRL_CUDA_CHECK(cudaStreamWaitEvent(st.side2, st.ev2[i], 0));
+  pdl_break(st.side2);
+  return DRL_OK;
+}
+static inline int join_side2_into(const Streams& st, int i, cudaStream_t into) {
+  if (!st.par || !st.side2) return DRL_OK;
+  DRL_CUDA_CHECK(cudaEventRecord(st.ev2[i], st.side2));
+  DRL_CUDA_CHECK(cudaStreamWaitEvent(into, st.ev2[i], 0));
+  pdl_break(into);
+  return DRL_OK;
+}
 static inline int join_from_side(const Streams& st, int i) {
   if (!st.par) return DRL_OK;
   DRL_CUDA_CHECK(cudaEventRecord(st.ev[i], st.side));

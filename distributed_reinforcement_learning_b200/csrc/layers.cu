@@ -117,9 +117,23 @@ int net_forward(const Streams& st, const ParamLayout& pl, const float* P, const 
   KERNEL("emb_fwd",
          emb_forward(s, P + pl.emb1_w, P + pl.emb1_b, P + pl.emb2_w, P + pl.emb2_b, act.e1, act.table, pl.A), 1);
   s = st.main;
+  bool late_images = false;   // side still carries the images only the backward pass reads when lstm_fwd is enqueued
   if (retile && mode >= 2) {
-    if (m16) DRL_TRY(net_retile16(side, pl, P, wi));
-    else DRL_TRY(net_retile(st.main, side, pl, P, wi));
+    if (m16 && st.par) {
+      // the LSTM forward image first; lstm_fwd waits for it (and the embedding table) only -- the three images of the
+      // backward pass (LSTM dgrad, two dCol) are joined at the end of the forward pass, long after they are done
+      prof_mark(side, "weight_retile");
+      DRL_TRY((launch_retile_b16<256, Fmt16>(side, PlainB{P + pl.lstm_w, Geo::G4, 0}, Geo::G4, Geo::XK, wi.img[3])));
+      DRL_CUDA_CHECK(cudaEventRecord(st.ev[1], side));
+      DRL_TRY((launch_retile_b16<128, Fmt16>(side, PlainBT{P + pl.lstm_w, Geo::G4, 0}, Geo::FLAT + Geo::EMB, Geo::G4, wi.img[4])));
+      DRL_TRY((launch_retile_b16<256, Fmt16>(side, PlainBT{P + pl.conv3_w, 64, 0}, 576, 64, wi.img[5])));
+      DRL_TRY((launch_retile_b16<256, Fmt16>(side, PlainBT{P + pl.conv2_w, 64, 0}, 512, 64, wi.img[6])));
+      late_images = true;
+    } else if (m16) {
+      DRL_TRY(net_retile16(side, pl, P, wi));
+    } else {
+      DRL_TRY(net_retile(st.main, side, pl, P, wi));
+    }
     n += 4;
   }
   if (retile && m16 && st.par) {
@@ -174,7 +188,12 @@ int net_forward(const Streams& st, const ParamLayout& pl, const float* P, const 
     if (m16) GEMM16("conv3_fwd", X64L, al, blp, ep, M * 49, 64, 576, 1, 576, 0);
     else GEMM_W("conv3_fwd", CfgBig, U64L, al, bl, blp, ep, M * 49, 64, 576, 1, 576, 0);
   }
-  DRL_TRY(join_from_side(st, 1));
+  if (late_images) {
+    DRL_CUDA_CHECK(cudaStreamWaitEvent(st.main, st.ev[1], 0));
+    pdl_break(st.main);
+  } else {
+    DRL_TRY(join_from_side(st, 1));
+  }
   // LSTM pre-activation z = [a3 | emb | h0] W  (split-K partial sums; bias added in the gate kernel) (:18-25)
   {
     LstmA al{act.a3, act.table, in.pa, in.h0, map};
@@ -207,6 +226,7 @@ int net_forward(const Streams& st, const ParamLayout& pl, const float* P, const 
   KERNEL("heads_out_fwd",
          heads_out_forward(s, act.hid2, act.hid2 + (size_t)M * Geo::HID, P + pl.actor3_w, P + pl.actor3_b,
                            P + pl.critic3_w, P + pl.critic3_b, act.logits, act.policy, act.value, M, pl.A), 1);
+  if (late_images) DRL_TRY(join_from_side(st, 1));   // the backward images: done ~70 us ago, keeps net_forward self-contained
   g_fwd_launches = n;
   return DRL_OK;
 }
@@ -229,8 +249,12 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, const
   KERNEL("heads_out_bwd",
          heads_out_backward(s, bw.dlogits, bw.dv, P + pl.actor3_w, P + pl.critic3_w, act.hid2,
                             act.hid2 + (size_t)M * Geo::HID, bw.dhid2, bw.dhid2 + (size_t)Mb * Geo::HID, Mb, A), 1);
-  DRL_TRY(fork_to_side(st, 0));     // dlogits / dv / dhid2 are ready: three weight gradients can start beside the chain
-  s = side;
+  // dlogits / dv / dhid2 are ready: three weight gradients can start beside the chain (on the second side lane if any)
+  const bool lane2 = st.par && st.side2 != nullptr;
+  const cudaStream_t small = lane2 ? st.side2 : side;
+  if (lane2) DRL_TRY(fork_to_side2(st, 0));
+  else DRL_TRY(fork_to_side(st, 0));
+  s = small;
   {  // d actor3 [256(+1), A]
     PlainAT al{act.hid2, Geo::HID, 0};
     PlainB bl{bw.dlogits, 32, 0};
@@ -256,8 +280,9 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, const
     EpReluMask ep{bw.dhid1, act.hid1, Geo::HID, (size_t)Mb * Geo::HID, (size_t)M * Geo::HID};
     GEMM_FFMA("heads_l2_dgrad", CfgSmall, al, bl, ep, Mb, Geo::HID, Geo::HID, 2, Geo::HID, 0);
   }
-  DRL_TRY(fork_to_side(st, 2));
-  s = side;
+  if (lane2) DRL_TRY(fork_to_side2(st, 1));
+  else DRL_TRY(fork_to_side(st, 2));
+  s = small;
   {  // d {actor1, critic1} = h1^T dhid1
     PlainAT al{act.h1, Geo::L, 0};
     PlainB bl{bw.dhid1, Geo::HID, (size_t)Mb * Geo::HID};
@@ -282,7 +307,9 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, const
     EpRaw<true> ep{G + pl.lstm_w, Geo::G4, 0, 1.0f, Geo::XK, Geo::G4};
     if (m16) GEMM16("lstm_wgrad", X256W, al, bl, ep, Geo::XK, Geo::G4, Mb, 1, Mb, 0);
     else GEMM("lstm_wgrad", CfgBig, U256, al, bl, ep, Geo::XK, Geo::G4, Mb, 1, Mb, 0);   // 29 x 4 = 116 CTAs: one wave
-    // the head gradients (earlier on this stream) and the LSTM gradient are now in the bucket: [lstm_w .. end)
+    // the head gradients (earlier on this stream, or on the second lane: joined here) and the LSTM gradient are now
+    // in the bucket: [lstm_w .. end)
+    if (lane2) DRL_TRY(join_side2_into(st, 2, side));
     if (st.par && st.ev_lstm_grads) DRL_CUDA_CHECK(cudaEventRecord(st.ev_lstm_grads, side));
   }
   s = st.main;

@@ -127,6 +127,8 @@ struct drl_learner {
   int peer_early_ctas = 64;   // grid of the early exchange instance (DRL_B200_PEER_EARLY_CTAS; 0 = no early part)
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done = nullptr;
   cudaEvent_t fj[8] = {};    // fork/join events between the compute and the side stream
+  cudaStream_t side2 = nullptr;   // second side lane (small head weight gradients), DRL_B200_SIDE2=0 disables
+  cudaEvent_t fj2[4] = {};
   bool par = true;           // run off-critical-path kernels on the side stream
   bool images_stale = true;  // weight images do not match the parameters (forward-only entry points rebuild them)
   float* params = nullptr;
@@ -228,6 +230,8 @@ Streams streams_of(const drl_learner* h) {
   st.side = h->side;
   for (int i = 0; i < 8; ++i) st.ev[i] = h->fj[i];
   st.par = h->par;
+  st.side2 = h->side2;
+  for (int i = 0; i < 4; ++i) st.ev2[i] = h->fj2[i];
   st.ev_lstm_grads = (h->peer_on && h->peer_early_ctas > 0) ? h->ev_lstm_grads : nullptr;
   return st;
 }
@@ -448,6 +452,13 @@ int drl_learner_create(const drl_learner_config* cfg, drl_learner** out) {
     DRL_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_xchg_done, cudaEventDisableTiming));
     if (const char* e = getenv("DRL_B200_PEER_EARLY_CTAS")) h->peer_early_ctas = atoi(e);
     for (int i = 0; i < 8; ++i) DRL_CUDA_CHECK(cudaEventCreateWithFlags(&h->fj[i], cudaEventDisableTiming));
+    {
+      const char* e = getenv("DRL_B200_SIDE2");
+      if (!(e && atoi(e) == 0)) {
+        DRL_CUDA_CHECK(cudaStreamCreateWithFlags(&h->side2, cudaStreamNonBlocking));
+        for (int i = 0; i < 4; ++i) DRL_CUDA_CHECK(cudaEventCreateWithFlags(&h->fj2[i], cudaEventDisableTiming));
+      }
+    }
     DRL_CUDA_CHECK(cudaEventCreate(&h->ev_start));
     DRL_CUDA_CHECK(cudaEventCreate(&h->ev_stop));
     DRL_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
@@ -590,6 +601,8 @@ int drl_learner_destroy(drl_learner* h) {
   if (h->ev_done) cudaEventDestroy(h->ev_done);
   for (auto e : h->ev_done_slot) if (e) cudaEventDestroy(e);
   for (int i = 0; i < 8; ++i) if (h->fj[i]) cudaEventDestroy(h->fj[i]);
+  for (int i = 0; i < 4; ++i) if (h->fj2[i]) cudaEventDestroy(h->fj2[i]);
+  if (h->side2) cudaStreamDestroy(h->side2);
   if (h->side) cudaStreamDestroy(h->side);
   if (h->xchg) cudaStreamDestroy(h->xchg);
   if (h->ev_lstm_grads) cudaEventDestroy(h->ev_lstm_grads);
