@@ -68,8 +68,8 @@ struct Conv1Tma {
 
 template <class EP>
 __global__ void __launch_bounds__(Conv1Tma::NT, 1)
-conv1_fwd_tma_kernel(const __grid_constant__ CUtensorMap fmap, const uint8_t* __restrict__ wimage, const EP ep, RowMap map,
-                     int nframes, int flags) {
+conv1_fwd_tma_kernel(const __grid_constant__ CUtensorMap fmap, const uint8_t* __restrict__ wimage,
+                     const float* __restrict__ wf32, const EP ep, RowMap map, int nframes, int flags) {
   pdl_prologue();
   using C = Conv1Tma;
   using TA = Umma16Tile<128, true>;
@@ -107,7 +107,10 @@ conv1_fwd_tma_kernel(const __grid_constant__ CUtensorMap fmap, const uint8_t* __
       umma::mbar_init(&acc_full[b], 1);
       umma::mbar_init(&acc_empty[b], C::EPI_WARPS * 32);
     }
-    umma::mbar_init(w_full, 1);
+    // weights: either ONE bulk copy of the pre-tiled image (expect_tx), or -- wf32 != nullptr -- the epilogue warps
+    // build the image from the fp32 HWIO weights themselves while the first frame slab is in flight: the step's first
+    // kernel then has no weight-image kernel in front of it (5 us at the head of every step)
+    umma::mbar_init(w_full, wf32 ? C::EPI_WARPS * 32 : 1);
     umma::fence_barrier_init();
   }
   if (warp == C::W_MMA) umma::tmem_alloc<C::TMEM_COLS>(tmem_ptr);
@@ -176,6 +179,25 @@ conv1_fwd_tma_kernel(const __grid_constant__ CUtensorMap fmap, const uint8_t* __
     // ================= EPILOGUE (warps 8..11: TMEM lane quarter = warp & 3) =================
     const int quarter = warp & 3;
     uint8_t* stg = smem + C::OFF_EPI + quarter * kEpiStageBytes;
+    if (wf32) {
+      // [K = 256][N = 32] fp32 -> per K tile of 64: rows 0..31 = fp16(w), rows 32..63 = fp16(w - hi) (K-major, swizzled):
+      // 1024 units of 8 consecutive k of one n; lanes = consecutive n (coalesced 128-byte rows of the HWIO matrix)
+      const int et = tid - C::CONV_WARPS * 32;
+      for (int u = et; u < 32 * 32; u += C::EPI_WARPS * 32) {
+        const int n = u & 31, kb = (u >> 5) * 8;
+        float x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = __ldg(wf32 + (size_t)(kb + i) * 32 + n);
+        uint4 h, l;
+        umma16::split8<umma16::F16>(make_float4(x[0], x[1], x[2], x[3]), make_float4(x[4], x[5], x[6], x[7]), h, l);
+        uint8_t* dst = wsm + (kb >> 6) * (2 * TB::BYTES);
+        const int off = TB::chunk_off(n, kb & 63);
+        *reinterpret_cast<uint4*>(dst + off) = h;
+        *reinterpret_cast<uint4*>(dst + TB::BYTES + off) = l;
+      }
+      umma::fence_proxy_async();
+      umma::mbar_arrive(w_full);
+    }
     uint32_t tile = 0;
     for (int mf = blockIdx.x; mf < nframes; mf += gridDim.x) {
       const int row_base = mf * C::PIX, row_end = row_base + C::PIX;
@@ -229,8 +251,10 @@ conv1_fwd_tma_kernel(const __grid_constant__ CUtensorMap fmap, const uint8_t* __
     // ================= TMA PRODUCER =================
     if (lane == 0) {
       umma::prefetch_tensormap(&fmap);
-      umma::mbar_arrive_expect_tx(w_full, C::W_BYTES);
-      umma::bulk_g2s(wsm, wimage, C::W_BYTES, w_full);
+      if (!wf32) {
+        umma::mbar_arrive_expect_tx(w_full, C::W_BYTES);
+        umma::bulk_g2s(wsm, wimage, C::W_BYTES, w_full);
+      }
       int fi = 0;
       for (int mf = blockIdx.x; mf < nframes; mf += gridDim.x, ++fi) {
         const int slot = fi & 1;
@@ -304,7 +328,7 @@ inline int conv1_frame_map(const uint8_t* frames, int nframes, CUtensorMap* out)
 
 template <class EP>
 inline int launch_conv1_fwd_tma(cudaStream_t s, const uint8_t* frames, int nframes, const RowMap& map, const uint8_t* wimage,
-                                const EP& ep) {
+                                const float* wf32, const EP& ep) {
   using Key = std::tuple<const uint8_t*, int>;
   static thread_local std::map<Key, CUtensorMap> cache;
   const Key key{frames, nframes};
@@ -322,7 +346,7 @@ inline int launch_conv1_fwd_tma(cudaStream_t s, const uint8_t* frames, int nfram
   }
   const int grid = std::min(nframes, device_sm_count());
   static const int flags = getenv("DRL_C1_FLAGS") ? atoi(getenv("DRL_C1_FLAGS")) : 0;   // experiments (see the kernel)
-  DRL_CUDA_CHECK((launch_k(kern, grid, Conv1Tma::NT, Conv1Tma::SMEM_BYTES, s, it->second, wimage, ep, map, nframes, flags)));
+  DRL_CUDA_CHECK((launch_k(kern, grid, Conv1Tma::NT, Conv1Tma::SMEM_BYTES, s, it->second, wimage, wf32, ep, map, nframes, flags)));
   return DRL_OK;
 }
 

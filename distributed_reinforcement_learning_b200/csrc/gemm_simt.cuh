@@ -43,8 +43,12 @@ struct SmemLayout {
   static constexpr int BYTES = 2 * (A_ELEMS + B_ELEMS) * 4;
 };
 
-template <class Cfg, class AL, class BL, class EP>
-__global__ void __launch_bounds__(Cfg::NT)
+// KS > 1: in-CTA split-K for the small, latency-bound dense layers (heads): KS thread groups of Cfg::NT threads each
+// own every KS-th K tile (their own shared-memory buffers, a named barrier per group), so the K tiles of one output
+// tile are loaded and multiplied concurrently instead of one after the other; the partial tiles are then summed by
+// group 0 in the fixed order 0..KS-1 (deterministic) before the unchanged epilogue.  KS = 1 is the original kernel.
+template <class Cfg, class AL, class BL, class EP, int KS = 1>
+__global__ void __launch_bounds__(Cfg::NT * KS)
 gemm_simt_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, int kchunk, int kstep) {
   pdl_prologue();
   constexpr int BM = Cfg::BM, BN = Cfg::BN, BK = Cfg::BK, TM = Cfg::TM, TN = Cfg::TN;
@@ -54,17 +58,24 @@ gemm_simt_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, int
   constexpr int SA = SL::SA, SB = SL::SB;
   constexpr int GA = BM * BK / 4 / NT, GB = BN * BK / 4 / NT;
 
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(16) float smem_all[];
+  const int grp = KS > 1 ? (int)threadIdx.x / NT : 0;
+  float* smem = smem_all + (size_t)grp * (2 * (SL::A_ELEMS + SL::B_ELEMS));
   float* As = smem;                       // 2 buffers
   float* Bs = smem + 2 * SL::A_ELEMS;     // 2 buffers
+  auto group_sync = [&]() {
+    if (KS == 1) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(NT) : "memory");
+  };
 
-  const int tid = threadIdx.x;
+  const int tid = KS > 1 ? (int)threadIdx.x % NT : (int)threadIdx.x;
   const int tx = tid % TX, ty = tid / TX;
   const int z = blockIdx.z;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int k0 = z * kstep;
   const int k1 = min(K, k0 + kchunk);
-  const int ntiles = (k1 - k0 + BK - 1) / BK;
+  const int ntiles_all = (k1 - k0 + BK - 1) / BK;
+  const int ntiles = KS > 1 ? (ntiles_all > grp ? (ntiles_all - grp + KS - 1) / KS : 0) : ntiles_all;   // this group's
 
   // ---- loader assignment: group g = tid + i*NT --------------------------------------
   // K-contig : row = g / (BK/4), kq = g % (BK/4)  -> smem [row][kq*4]
@@ -109,7 +120,7 @@ gemm_simt_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, int
 
   float4 ra[GA], rb[GB];
   auto gload = [&](int t) {
-    const int kb = k0 + t * BK;
+    const int kb = k0 + (grp + t * KS) * BK;
 #pragma unroll
     for (int i = 0; i < GA; ++i) {
       const int k = kb + a_k[i];
@@ -141,7 +152,7 @@ gemm_simt_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, int
     gload(0);
     sstore(0);
   }
-  __syncthreads();
+  group_sync();
 
   for (int t = 0; t < ntiles; ++t) {
     const int buf = t & 1;
@@ -200,7 +211,35 @@ gemm_simt_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, int
     }
 
     if (t + 1 < ntiles) sstore(buf ^ 1);
+    group_sync();
+  }
+
+  if (KS > 1) {
+    // partial tiles of groups 1..KS-1 -> their own (now idle) buffers, float4 e of thread tid at [(e * NT + tid)]
+    static_assert(KS == 1 || 2 * (SL::A_ELEMS + SL::B_ELEMS) >= NT * TM * TN + BN, "partial tile must fit the group's buffers");
+    if (grp > 0) {
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; j += 4)
+          *reinterpret_cast<float4*>(smem + ((i * TN + j) / 4 * NT + tid) * 4) =
+              make_float4(acc[i][j], acc[i][j + 1], acc[i][j + 2], acc[i][j + 3]);
+      if (EP::kColSum && !BKc && tid < BN) smem[NT * TM * TN + tid] = colsum;
+    }
     __syncthreads();
+    if (grp > 0) return;
+#pragma unroll 1
+    for (int g = 1; g < KS; ++g) {
+      const float* part = smem_all + (size_t)g * (2 * (SL::A_ELEMS + SL::B_ELEMS));
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; j += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(part + ((i * TN + j) / 4 * NT + tid) * 4);
+          acc[i][j] += v.x; acc[i][j + 1] += v.y; acc[i][j + 2] += v.z; acc[i][j + 3] += v.w;
+        }
+      if (EP::kColSum && !BKc && tid < BN) colsum += part[NT * TM * TN + tid];
+    }
   }
 
   // ---- epilogue ---------------------------------------------------------------------
@@ -240,14 +279,15 @@ gemm_simt_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, int
   }
 }
 
-template <class Cfg, class AL, class BL, class EP>
+template <class Cfg, int KS = 1, class AL, class BL, class EP>
 inline int launch_gemm_simt(cudaStream_t s, const AL& al, const BL& bl, const EP& ep, int M, int N, int K,
                             int zcount, int kchunk, int kstep) {
   using SL = SmemLayout<Cfg, AL::kContigK, BL::kContigK>;
+  static_assert(SL::BYTES * KS <= 227 * 1024 && Cfg::NT * KS <= 1024, "in-CTA split-K does not fit");
   static bool attr_done = false;   // per instantiation
-  auto kern = gemm_simt_kernel<Cfg, AL, BL, EP>;
+  auto kern = gemm_simt_kernel<Cfg, AL, BL, EP, KS>;
   if (!attr_done) {
-    DRL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::BYTES));
+    DRL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::BYTES * KS));
     attr_done = true;
   }
   if ((AL::kContigK || BL::kContigK) && (K % 4 != 0 || kchunk % 4 != 0)) {
@@ -255,7 +295,7 @@ inline int launch_gemm_simt(cudaStream_t s, const AL& al, const BL& bl, const EP
     return DRL_ERR_INVALID;
   }
   dim3 grid(cdiv(M, Cfg::BM), cdiv(N, Cfg::BN), zcount);
-  DRL_CUDA_CHECK((launch_k(kern, grid, Cfg::NT, SL::BYTES, s, al, bl, ep, M, N, K, kchunk, kstep)));
+  DRL_CUDA_CHECK((launch_k(kern, grid, Cfg::NT * KS, SL::BYTES * KS, s, al, bl, ep, M, N, K, kchunk, kstep)));
   return DRL_OK;
 }
 

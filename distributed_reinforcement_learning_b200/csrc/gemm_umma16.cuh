@@ -118,8 +118,10 @@ struct Umma16Tile {
   __device__ static __forceinline__ int kslice_off(int j) { return KMAJOR ? j * 32 : j * 2 * SBO; }
 };
 
-template <int BN_, int STAGES_, int MINB_ = 1, int PW_ = 4, int LW_ = 0, class AF_ = umma16::BF16, class BF_ = umma16::BF16>
+template <int BN_, int STAGES_, int MINB_ = 1, int PW_ = 4, int LW_ = 0, class AF_ = umma16::BF16, class BF_ = umma16::BF16,
+          int PFD_ = 0>
 struct Umma16Cfg {
+  static constexpr int PFD = PFD_;   // register prefetch ring depth in 32-wide K sub-tiles (0: 4 / 3 / 2 by operand kind)
   static constexpr int BM = 128, BN = BN_, BK = 64, SUBK = 32, STAGES = STAGES_, MINB = MINB_;
   static constexpr int PW = PW_, LW = LW_;
   static constexpr int NPROD = PW * 32;
@@ -378,7 +380,7 @@ gemm_umma16_kernel(const AL al, const BL bl, const EP ep, int M, int N, int K, i
       if (tid == 0) TR(2000 + g);
     };
 
-    constexpr int PF = A16 ? 4 : (BPT ? 3 : 2);   // register prefetch ring, in sub-tiles
+    constexpr int PF = Cfg::PFD > 0 ? Cfg::PFD : (A16 ? 4 : (BPT ? 3 : 2));   // register prefetch ring, in sub-tiles
     const int nsub = 2 * ntiles;
     ARaw ra[PF][UA][AR];
     float4 rb[PF][UB][2];
@@ -536,6 +538,50 @@ __global__ void __launch_bounds__(256) retile_b16_kernel(const BL bl, int N, int
   const int off = TB::chunk_off(r, c * 8);
   *reinterpret_cast<uint4*>(dst + off) = h;
   *reinterpret_cast<uint4*>(dst + TB::BYTES + off) = l;
+}
+
+// The same image from an operand whose ROW index is the contiguous one in memory (kContigK == false: x^T, dz^T, [k][n]
+// weights): a thread owns 4 consecutive rows x 8 consecutive k -- eight 128-bit loads (lanes = consecutive row groups of one k:
+// coalesced), every loaded value used, four hi + four lo 16-byte chunks stored.  retile_b16_kernel spends one thread per
+// (row, 8 k) and uses one element of each float4 it loads.
+template <int BN, class F, class BL>
+__global__ void __launch_bounds__(256) retile_t16_kernel(const BL bl, int N, int K, int ktiles, int ntn,
+                                                          uint8_t* __restrict__ image) {
+  static_assert(!BL::kContigK, "transposing variant: the loader's row index is contiguous in memory");
+  pdl_prologue();
+  using TB = Umma16Tile<BN, true>;
+  constexpr int UPT = (BN / 4) * 8;                  // (4-row group, 8-k group) units per tile
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long long)ntn * ktiles * UPT) return;
+  const int tile = (int)(g / UPT), lu = (int)(g % UPT);
+  const int nt = tile / ktiles, kt = tile - nt * ktiles;
+  const int rq = lu % (BN / 4), c = lu / (BN / 4);
+  const int n = nt * BN + rq * 4, kb = kt * 64 + c * 8;
+  float x[8][4];
+  const typename BL::Row row = bl.row(0, n < N ? n : -1);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 v = (n < N && kb + i < K) ? bl.load(row, kb + i) : zero4();
+    x[i][0] = v.x; x[i][1] = v.y; x[i][2] = v.z; x[i][3] = v.w;
+  }
+  uint8_t* dst = image + (size_t)tile * (2 * TB::BYTES);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 h, l;
+    umma16::split8<F>(make_float4(x[0][j], x[1][j], x[2][j], x[3][j]), make_float4(x[4][j], x[5][j], x[6][j], x[7][j]), h, l);
+    if (n + j >= N) { h = make_uint4(0u, 0u, 0u, 0u); l = h; }
+    const int off = TB::chunk_off(rq * 4 + j, c * 8);
+    *reinterpret_cast<uint4*>(dst + off) = h;
+    *reinterpret_cast<uint4*>(dst + TB::BYTES + off) = l;
+  }
+}
+
+template <int BN, class F, class BL>
+inline int launch_retile_t16(cudaStream_t s, const BL& bl, int N, int K, uint8_t* image) {
+  const int ntn = cdiv(N, BN), ktiles = cdiv(K, 64);
+  const long long units = (long long)ntn * ktiles * (BN / 4) * 8;
+  DRL_CUDA_CHECK((launch_k(retile_t16_kernel<BN, F, BL>, (unsigned)cdiv64(units, 256), 256, 0, s, bl, N, K, ktiles, ntn, image)));
+  return DRL_OK;
 }
 
 template <int BN>

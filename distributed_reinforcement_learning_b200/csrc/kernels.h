@@ -53,6 +53,9 @@ struct Acts {            // forward activations, time-major rows m = t*B + b, M 
   float* logits;         // [M,A]
   float* policy;         // [M,A]
   float* value;          // [M]
+  // math mode 5, bulk-fed lstm_wgrad (gemm_bulk16.cuh): x^T = [a3|emb|h0]^T as a 16-bit operand image, nullptr = gather path
+  uint8_t* img_xt = nullptr;   // x^T : rows = features (3648) x K = Mb rows -- A operand of lstm_wgrad
+  int img_rows = 0;            // M the images were sized for
 };
 
 struct Bwd {             // backward workspace, Mb = B*(T-2) rows
@@ -62,6 +65,7 @@ struct Bwd {             // backward workspace, Mb = B*(T-2) rows
   float* dhid1;          // [2][Mb,256]
   float* dh_part;        // [2][Mb,256] actor and critic contributions to dL/dh1
   float* dz;             // [Mb,1024]
+  uint8_t* img_dzt = nullptr;  // dz^T : rows n (1024) x K = Mb rows  -- B operand of the bulk-fed lstm_wgrad (see Acts::img_xt)
   float* da3;            // [Mb,3136]
   float* du;             // [Mb,256]
   float* dpre2;          // [A,256]
@@ -120,8 +124,8 @@ struct Streams {
   cudaEvent_t ev[8];
   bool par;
   // optional second side lane (IMPALA handle): the four small, latency-bound head weight gradients run here so that they
-  // do not sit in front of lstm_wgrad / the conv weight gradients on `side` (tools/timeline.py: the serial side stream
-  // ended 35 us after the main chain).  nullptr: everything stays on `side`.
+  // do not sit in front of lstm_wgrad / the conv weight gradients on `side` (tools/timeline.py, profiles/r02_timeline_*).
+  // nullptr: everything stays on `side`.
   cudaStream_t side2 = nullptr;
   cudaEvent_t ev2[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_lstm_grads = nullptr;   // backward: recorded on the side stream once the head and LSTM weight gradients
@@ -133,6 +137,8 @@ int net_forward(const Streams& st, const ParamLayout& pl, const float* params, c
 int net_backward(const Streams& st, const ParamLayout& pl, const float* params, const WeightImages& wi, float* grads,
                  const Inputs& in, const Acts& act, const Bwd& bwd, int B, int T, int mode);
 size_t wgrad_partial_floats(int B, int T);
+// bytes of the operand images of the bulk-fed lstm_wgrad: which = 1 x^T (K = Mb), 3 dz^T (K = Mb)
+size_t lstm_image_bytes(int which, int M, int Mb);
 int forward_launch_count();
 int backward_launch_count();
 

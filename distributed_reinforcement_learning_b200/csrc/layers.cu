@@ -52,6 +52,12 @@ size_t wgrad_partial_floats(int B, int T) {
   return std::max(mx, (size_t)16 * 32 * 256);   // also the scratch of emb_backward (kEmbChunks * A * 256)
 }
 
+size_t lstm_image_bytes(int which, int M, int Mb) {
+  (void)M;
+  return which == 1 ? operand_image16_bytes<128>(Geo::XK, Mb)     // x^T  (A of lstm_wgrad)
+                    : operand_image16_bytes<256>(Geo::G4, Mb);    // dz^T (B of lstm_wgrad)
+}
+
 void weight_image_sizes(size_t (&b)[WeightImages::kCount]) {
   b[0] = weight_image_bytes<32>(32, 256);
   b[1] = weight_image_bytes<64>(64, 512);
@@ -99,14 +105,23 @@ int net_forward(const Streams& st, const ParamLayout& pl, const float* P, const 
   // weight images of this step's parameters, all on the side stream: the conv2/conv3 forward ones first (main waits
   // for them behind conv1), the LSTM / dgrad ones behind the embedding table (joined before lstm_fwd)
   const bool m16 = mode == 5;
+  static const bool heads_tc = !(getenv("DRL_B200_HEADS_TC") && atoi(getenv("DRL_B200_HEADS_TC")) == 0);   // head layers on tcgen05 (0: FFMA)
+  // math mode 5: conv1 is the frame-resident TMA kernel (conv1_tma.cuh), which builds its 32 KB weight image itself;
+  // DRL_B200_CONV1_GATHER=1 keeps the generic gather-GEMM, DRL_B200_C1_WIMG=1 the pre-tiled image (one more kernel in
+  // front of the step's first kernel)
+  static const bool c1_gather = getenv("DRL_B200_CONV1_GATHER") != nullptr;
+  static const bool c1_wimg = c1_gather || getenv("DRL_B200_C1_WIMG") != nullptr;
   if (retile && m16) {
     prof_mark(s, "weight_retile");
-    DRL_TRY((launch_retile_b16<32, FmtC1>(s, PlainB{P + pl.conv1_w, 32, 0}, 32, 256, wi.img[0])));
-    if (st.par) DRL_CUDA_CHECK(cudaEventRecord(st.ev[2], side));          // conv1 waits for its (tiny) image
+    if (c1_wimg) {
+      DRL_TRY((launch_retile_b16<32, FmtC1>(s, PlainB{P + pl.conv1_w, 32, 0}, 32, 256, wi.img[0])));
+      if (st.par) DRL_CUDA_CHECK(cudaEventRecord(st.ev[2], side));        // conv1 waits for its (tiny) image
+      ++n;
+    }
     DRL_TRY((launch_retile_b16<64, Fmt16>(s, PlainB{P + pl.conv2_w, 64, 0}, 64, 512, wi.img[1])));
     DRL_TRY((launch_retile_b16<64, Fmt16>(s, PlainB{P + pl.conv3_w, 64, 0}, 64, 576, wi.img[2])));
     if (st.par) DRL_CUDA_CHECK(cudaEventRecord(st.ev[7], side));          // conv2 / conv3 images (main waits behind conv1)
-    n += 3;
+    n += 2;
   } else if (retile && mode >= 2) {
     prof_mark(s, "weight_retile");
     DRL_TRY((launch_retile_b<64>(s, PlainB{P + pl.conv2_w, 64, 0}, 64, 512, wi.img[1])));
@@ -125,10 +140,7 @@ int net_forward(const Streams& st, const ParamLayout& pl, const float* P, const 
       prof_mark(side, "weight_retile");
       DRL_TRY((launch_retile_b16<256, Fmt16>(side, PlainB{P + pl.lstm_w, Geo::G4, 0}, Geo::G4, Geo::XK, wi.img[3])));
       DRL_CUDA_CHECK(cudaEventRecord(st.ev[1], side));
-      DRL_TRY((launch_retile_b16<128, Fmt16>(side, PlainBT{P + pl.lstm_w, Geo::G4, 0}, Geo::FLAT + Geo::EMB, Geo::G4, wi.img[4])));
-      DRL_TRY((launch_retile_b16<256, Fmt16>(side, PlainBT{P + pl.conv3_w, 64, 0}, 576, 64, wi.img[5])));
-      DRL_TRY((launch_retile_b16<256, Fmt16>(side, PlainBT{P + pl.conv2_w, 64, 0}, 512, 64, wi.img[6])));
-      late_images = true;
+      late_images = true;   // LSTM dgrad + two dCol images: behind lstm_gates_fwd, in the shadow of the small head kernels
     } else if (m16) {
       DRL_TRY(net_retile16(side, pl, P, wi));
     } else {
@@ -136,7 +148,7 @@ int net_forward(const Streams& st, const ParamLayout& pl, const float* P, const 
     }
     n += 4;
   }
-  if (retile && m16 && st.par) {
+  if (retile && m16 && st.par && c1_wimg) {
     DRL_CUDA_CHECK(cudaStreamWaitEvent(st.main, st.ev[2], 0));
     pdl_break(st.main);
   }
@@ -145,11 +157,9 @@ int net_forward(const Streams& st, const ParamLayout& pl, const float* P, const 
     Conv1A al{in.frames, map};
     PlainB bl{P + pl.conv1_w, 32, 0};
     EpConv1 ep{act.a1, 32, P + pl.conv1_b, tma ? act.a1_lo : nullptr};
-    // math mode 5: frame-resident TMA kernel (conv1_tma.cuh); DRL_B200_CONV1_GATHER=1 keeps the generic gather-GEMM
-    static const bool c1_gather = getenv("DRL_B200_CONV1_GATHER") != nullptr;
     if (m16 && !c1_gather) {
       prof_mark(s, "conv1_fwd");
-      DRL_TRY(launch_conv1_fwd_tma(s, in.frames, M, map, wi.img[0], ep));
+      DRL_TRY(launch_conv1_fwd_tma(s, in.frames, M, map, wi.img[0], c1_wimg ? nullptr : P + pl.conv1_w, ep));
       ++n;
     } else if (m16) {
       PretiledB<PlainB> blp{wi.img[0], 256 / 64};
@@ -171,8 +181,10 @@ int net_forward(const Streams& st, const ParamLayout& pl, const float* P, const 
     PlainB bl{P + pl.conv2_w, 64, 0};
     PretiledB<PlainB> blp{wi.img[1], m16 ? 512 / 64 : 512 / 32};
     EpBiasAct<true, true> ep{act.a2, 64, 0, P + pl.conv2_b, 0, 1.0f};
-    static const int c2f = getenv("DRL_B200_C2F") ? atoi(getenv("DRL_B200_C2F")) : 0;
+    static const int c2f = getenv("DRL_B200_C2F") ? atoi(getenv("DRL_B200_C2F")) : 2;
     if (m16 && c2f == 1) GEMM16("conv2_fwd", X64L8, al, blp, ep, M * 81, 64, 512, 1, 512, 0);
+    else if (m16 && c2f == 2) GEMM16("conv2_fwd", X64L8x2, al, blp, ep, M * 81, 64, 512, 1, 512, 0);
+    else if (m16 && c2f == 3) GEMM16("conv2_fwd", X64L8x2p4, al, blp, ep, M * 81, 64, 512, 1, 512, 0);
     else if (m16) GEMM16("conv2_fwd", X64L, al, blp, ep, M * 81, 64, 512, 1, 512, 0);
     else GEMM_W("conv2_fwd", CfgBig, U64L, al, bl, blp, ep, M * 81, 64, 512, 1, 512, 0);
   }
@@ -185,7 +197,10 @@ int net_forward(const Streams& st, const ParamLayout& pl, const float* P, const 
     PlainB bl{P + pl.conv3_w, 64, 0};
     PretiledB<PlainB> blp{wi.img[2], m16 ? 576 / 64 : 576 / 32};
     EpBiasAct<true, true> ep{act.a3, 64, 0, P + pl.conv3_b, 0, 1.0f};
-    if (m16) GEMM16("conv3_fwd", X64L, al, blp, ep, M * 49, 64, 576, 1, 576, 0);
+    static const int c3f = getenv("DRL_B200_C2F") ? atoi(getenv("DRL_B200_C2F")) : 2;
+    if (m16 && c3f == 2) GEMM16("conv3_fwd", X64L8x2, al, blp, ep, M * 49, 64, 576, 1, 576, 0);
+    else if (m16 && c3f == 3) GEMM16("conv3_fwd", X64L8x2p4, al, blp, ep, M * 49, 64, 576, 1, 576, 0);
+    else if (m16) GEMM16("conv3_fwd", X64L, al, blp, ep, M * 49, 64, 576, 1, 576, 0);
     else GEMM_W("conv3_fwd", CfgBig, U64L, al, bl, blp, ep, M * 49, 64, 576, 1, 576, 0);
   }
   if (late_images) {
@@ -211,17 +226,27 @@ int net_forward(const Streams& st, const ParamLayout& pl, const float* P, const 
                             T), 1);
   // heads (fully_connected, :27-30,40-41): z = 0 actor, z = 1 critic
   const size_t head_stride = (size_t)(pl.critic1_w - pl.actor1_w);
+  if (late_images) {
+    // the three images only the backward pass reads (~25 us of memory-bound work) would compete with conv2_fwd / conv3_fwd
+    // for the SMs if launched with the others; the head layers that follow leave most of the GPU idle
+    DRL_TRY(fork_to_side(st, 3));
+    DRL_TRY((launch_retile_b16<128, Fmt16>(side, PlainBT{P + pl.lstm_w, Geo::G4, 0}, Geo::FLAT + Geo::EMB, Geo::G4, wi.img[4])));
+    DRL_TRY((launch_retile_b16<256, Fmt16>(side, PlainBT{P + pl.conv3_w, 64, 0}, 576, 64, wi.img[5])));
+    DRL_TRY((launch_retile_b16<256, Fmt16>(side, PlainBT{P + pl.conv2_w, 64, 0}, 512, 64, wi.img[6])));
+  }
   {
     PlainA al{act.h1, Geo::L, 0};
     PlainB bl{P + pl.actor1_w, Geo::HID, head_stride};
     EpBiasAct<true, true> ep{act.hid1, Geo::HID, (size_t)M * Geo::HID, P + pl.actor1_b, head_stride, 1.0f};
-    GEMM_FFMA("heads_l1_fwd", CfgSmall, al, bl, ep, M, Geo::HID, Geo::L, 2, Geo::L, 0);
+    if (m16 && heads_tc) GEMM16("heads_l1_fwd", XH, al, bl, ep, M, Geo::HID, Geo::L, 2, Geo::L, 0);
+    else GEMM_FFMA("heads_l1_fwd", CfgSmall, al, bl, ep, M, Geo::HID, Geo::L, 2, Geo::L, 0);
   }
   {
     PlainA al{act.hid1, Geo::HID, (size_t)M * Geo::HID};
     PlainB bl{P + pl.actor2_w, Geo::HID, head_stride};
     EpBiasAct<true, true> ep{act.hid2, Geo::HID, (size_t)M * Geo::HID, P + pl.actor2_b, head_stride, 1.0f};
-    GEMM_FFMA("heads_l2_fwd", CfgSmall, al, bl, ep, M, Geo::HID, Geo::HID, 2, Geo::HID, 0);
+    if (m16 && heads_tc) GEMM16("heads_l2_fwd", XH, al, bl, ep, M, Geo::HID, Geo::HID, 2, Geo::HID, 0);
+    else GEMM_FFMA("heads_l2_fwd", CfgSmall, al, bl, ep, M, Geo::HID, Geo::HID, 2, Geo::HID, 0);
   }
   KERNEL("heads_out_fwd",
          heads_out_forward(s, act.hid2, act.hid2 + (size_t)M * Geo::HID, P + pl.actor3_w, P + pl.actor3_b,
@@ -236,6 +261,7 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, const
   PdlRegionOff pdl_region;   // DRL_B200_PDL=2: no early launches while the side stream competes for the same SMs
   if (mode == 4) mode = 2;
   const bool m16 = mode == 5;
+  static const bool heads_tc = !(getenv("DRL_B200_HEADS_TC") && atoi(getenv("DRL_B200_HEADS_TC")) == 0);   // head layers on tcgen05 (0: FFMA)
   cudaStream_t s = st.main;
   const cudaStream_t side = st.par ? st.side : st.main;
   const int M = B * T;
@@ -249,6 +275,15 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, const
   KERNEL("heads_out_bwd",
          heads_out_backward(s, bw.dlogits, bw.dv, P + pl.actor3_w, P + pl.critic3_w, act.hid2,
                             act.hid2 + (size_t)M * Geo::HID, bw.dhid2, bw.dhid2 + (size_t)Mb * Geo::HID, Mb, A), 1);
+  const bool lbulk = m16 && act.img_xt != nullptr && bw.img_dzt != nullptr && M <= act.img_rows;   // bulk-fed lstm_wgrad
+  if (lbulk) {
+    // x^T as an operand image (A of lstm_wgrad): depends on the forward pass only -> side stream, in the shadow of the
+    // small head kernels
+    DRL_TRY(fork_to_side(st, 0));
+    prof_mark(side, "lstm_xt_image");
+    DRL_TRY((launch_retile_t16<128, Fmt16>(side, LstmAT{act.a3, act.table, in.pa, in.h0, map}, Geo::XK, Mb, act.img_xt)));
+    ++n;
+  }
   // dlogits / dv / dhid2 are ready: three weight gradients can start beside the chain (on the second side lane if any)
   const bool lane2 = st.par && st.side2 != nullptr;
   const cudaStream_t small = lane2 ? st.side2 : side;
@@ -259,26 +294,27 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, const
     PlainAT al{act.hid2, Geo::HID, 0};
     PlainB bl{bw.dlogits, 32, 0};
     EpRaw<true> ep{G + pl.actor3_w, A, 0, 1.0f, Geo::HID, A};
-    GEMM_FFMA("actor3_wgrad", CfgSmall, al, bl, ep, Geo::HID, 32, Mb, 1, Mb, 0);
+    GEMM_FFMA_KS("actor3_wgrad", CfgSmall, 3, al, bl, ep, Geo::HID, 32, Mb, 1, Mb, 0);
   }
   {  // d critic3 [256(+1), 1]
     PlainAT al{act.hid2 + (size_t)M * Geo::HID, Geo::HID, 0};
     PlainB bl{bw.dv, 32, 0};
     EpRaw<true> ep{G + pl.critic3_w, 1, 0, 1.0f, Geo::HID, 1};
-    GEMM_FFMA("critic3_wgrad", CfgSmall, al, bl, ep, Geo::HID, 32, Mb, 1, Mb, 0);
+    GEMM_FFMA_KS("critic3_wgrad", CfgSmall, 3, al, bl, ep, Geo::HID, 32, Mb, 1, Mb, 0);
   }
   {  // d {actor2, critic2} = hid1^T dhid2
     PlainAT al{act.hid1, Geo::HID, (size_t)M * Geo::HID};
     PlainB bl{bw.dhid2, Geo::HID, (size_t)Mb * Geo::HID};
     EpRaw<true> ep{G + pl.actor2_w, Geo::HID, head_stride, 1.0f, Geo::HID, Geo::HID};
-    GEMM_FFMA("heads_l2_wgrad", CfgSmall, al, bl, ep, Geo::HID, Geo::HID, Mb, 2, Mb, 0);
+    GEMM_FFMA_KS("heads_l2_wgrad", CfgSmall, 3, al, bl, ep, Geo::HID, Geo::HID, Mb, 2, Mb, 0);
   }
   s = st.main;
   {  // dhid1 = dhid2 W2^T * relu'(hid1)
     PlainA al{bw.dhid2, Geo::HID, (size_t)Mb * Geo::HID};
     PlainBT bl{P + pl.actor2_w, Geo::HID, head_stride};
     EpReluMask ep{bw.dhid1, act.hid1, Geo::HID, (size_t)Mb * Geo::HID, (size_t)M * Geo::HID};
-    GEMM_FFMA("heads_l2_dgrad", CfgSmall, al, bl, ep, Mb, Geo::HID, Geo::HID, 2, Geo::HID, 0);
+    if (m16 && heads_tc) GEMM16("heads_l2_dgrad", XH, al, bl, ep, Mb, Geo::HID, Geo::HID, 2, Geo::HID, 0);
+    else GEMM_FFMA_KS("heads_l2_dgrad", CfgSmall, 4, al, bl, ep, Mb, Geo::HID, Geo::HID, 2, Geo::HID, 0);
   }
   if (lane2) DRL_TRY(fork_to_side2(st, 1));
   else DRL_TRY(fork_to_side(st, 2));
@@ -287,14 +323,15 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, const
     PlainAT al{act.h1, Geo::L, 0};
     PlainB bl{bw.dhid1, Geo::HID, (size_t)Mb * Geo::HID};
     EpRaw<true> ep{G + pl.actor1_w, Geo::HID, head_stride, 1.0f, Geo::L, Geo::HID};
-    GEMM_FFMA("heads_l1_wgrad", CfgSmall, al, bl, ep, Geo::L, Geo::HID, Mb, 2, Mb, 0);
+    GEMM_FFMA_KS("heads_l1_wgrad", CfgSmall, 3, al, bl, ep, Geo::L, Geo::HID, Mb, 2, Mb, 0);
   }
   s = st.main;
   {  // dh1 contributions (actor, critic) = dhid1 W1^T ; summed in the gate kernel
     PlainA al{bw.dhid1, Geo::HID, (size_t)Mb * Geo::HID};
     PlainBT bl{P + pl.actor1_w, Geo::HID, head_stride};
     EpRaw<false> ep{bw.dh_part, Geo::L, (size_t)Mb * Geo::L, 1.0f, 0, Geo::L};
-    GEMM_FFMA("heads_l1_dgrad", CfgSmall, al, bl, ep, Mb, Geo::L, Geo::HID, 2, Geo::HID, 0);
+    if (m16 && heads_tc) GEMM16("heads_l1_dgrad", XH, al, bl, ep, Mb, Geo::L, Geo::HID, 2, Geo::HID, 0);
+    else GEMM_FFMA_KS("heads_l1_dgrad", CfgSmall, 4, al, bl, ep, Mb, Geo::L, Geo::HID, 2, Geo::HID, 0);
   }
   // ---- LSTM cell ---------------------------------------------------------------------------
   KERNEL("lstm_gates_bwd",
@@ -305,7 +342,20 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, const
     LstmAT al{act.a3, act.table, in.pa, in.h0, map};
     PlainB bl{bw.dz, Geo::G4, 0};
     EpRaw<true> ep{G + pl.lstm_w, Geo::G4, 0, 1.0f, Geo::XK, Geo::G4};
-    if (m16) GEMM16("lstm_wgrad", X256W, al, bl, ep, Geo::XK, Geo::G4, Mb, 1, Mb, 0);
+    static const bool lw3 = getenv("DRL_B200_LW3") != nullptr;
+    if (lbulk) {
+      const int ktm = cdiv(Mb, 64);
+      prof_mark(s, "lstm_dzt_image");
+      DRL_TRY((launch_retile_t16<256, Fmt16>(s, bl, Geo::G4, Mb, bw.img_dzt)));
+      // bias gradient = column sums of dz (row XK of [w; b]), fixed order
+      DRL_TRY(splitk_reduce(s, bw.dz, Geo::G4, Mb, G + pl.lstm_w + (size_t)Geo::XK * Geo::G4, Geo::G4));
+      prof_mark(s, "lstm_wgrad");
+      EpRaw<false> epw{G + pl.lstm_w, Geo::G4, 0, 1.0f, Geo::XK, Geo::G4};
+      DRL_TRY((launch_gemm_bulk16<BK256>(s, ImageOp{act.img_xt, ktm}, ImageOp{bw.img_dzt, ktm}, epw, Geo::XK, Geo::G4, Mb,
+                                         1, Mb, 0)));
+      n += 3;
+    } else if (m16 && lw3) GEMM16("lstm_wgrad", X256W3, al, bl, ep, Geo::XK, Geo::G4, Mb, 1, Mb, 0);
+    else if (m16) GEMM16("lstm_wgrad", X256W, al, bl, ep, Geo::XK, Geo::G4, Mb, 1, Mb, 0);
     else GEMM("lstm_wgrad", CfgBig, U256, al, bl, ep, Geo::XK, Geo::G4, Mb, 1, Mb, 0);   // 29 x 4 = 116 CTAs: one wave
     // the head gradients (earlier on this stream, or on the second lane: joined here) and the LSTM gradient are now
     // in the bucket: [lstm_w .. end)
@@ -334,7 +384,10 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, const
     Conv3WA al{act.a2, map};
     PlainB bl{bw.da3, 64, 0};
     EpRaw<true> ep{bw.wg_part, 64, slab, 1.0f, 576, 64};
-    if (m16) GEMM16("conv3_wgrad", X64W, al, bl, ep, 576, 64, Mb * 49, sp.splits, sp.kchunk, sp.kchunk);
+    static const int cw8 = getenv("DRL_B200_CW8") ? atoi(getenv("DRL_B200_CW8")) : 1;
+    if (m16 && cw8 == 2) GEMM16("conv3_wgrad", X64W8x2p3, al, bl, ep, 576, 64, Mb * 49, sp.splits, sp.kchunk, sp.kchunk);
+    else if (m16 && cw8) GEMM16("conv3_wgrad", X64W8x2, al, bl, ep, 576, 64, Mb * 49, sp.splits, sp.kchunk, sp.kchunk);
+    else if (m16) GEMM16("conv3_wgrad", X64W, al, bl, ep, 576, 64, Mb * 49, sp.splits, sp.kchunk, sp.kchunk);
     else GEMM("conv3_wgrad", CfgBig, U64, al, bl, ep, 576, 64, Mb * 49, sp.splits, sp.kchunk, sp.kchunk);
     KERNEL("conv3_wgrad_reduce", splitk_reduce(s, bw.wg_part, slab, sp.splits, G + pl.conv3_w, slab), 1);
   }
@@ -377,7 +430,10 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, const
     Conv2WA al{act.a1, map};
     PlainB bl{bw.da2, 64, 0};
     EpRaw<true> ep{bw.wg_part, 64, slab, 1.0f, 512, 64};
-    if (m16) GEMM16("conv2_wgrad", X64W, al, bl, ep, 512, 64, Mb * 81, sp.splits, sp.kchunk, sp.kchunk);
+    static const int cw8 = getenv("DRL_B200_CW8") ? atoi(getenv("DRL_B200_CW8")) : 1;
+    if (m16 && cw8 == 2) GEMM16("conv2_wgrad", X64W8x2p3, al, bl, ep, 512, 64, Mb * 81, sp.splits, sp.kchunk, sp.kchunk);
+    else if (m16 && cw8) GEMM16("conv2_wgrad", X64W8x2, al, bl, ep, 512, 64, Mb * 81, sp.splits, sp.kchunk, sp.kchunk);
+    else if (m16) GEMM16("conv2_wgrad", X64W, al, bl, ep, 512, 64, Mb * 81, sp.splits, sp.kchunk, sp.kchunk);
     else GEMM("conv2_wgrad", CfgBig, U64, al, bl, ep, 512, 64, Mb * 81, sp.splits, sp.kchunk, sp.kchunk);
     KERNEL("conv2_wgrad_reduce", splitk_reduce(s, bw.wg_part, slab, sp.splits, G + pl.conv2_w, slab), 1);
   }
@@ -423,6 +479,7 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, const
     GEMM("conv1_wgrad", CfgWg1, U32, al, bl, ep, 256, 32, Mb * 400, sp.splits, sp.kchunk, sp.kchunk);
     KERNEL("conv1_wgrad_reduce", splitk_reduce(s, bw.wg_part2, slab, sp.splits, G + pl.conv1_w, slab), 1);
   }
+  if (lane2) DRL_TRY(join_side2_into(st, 2, st.main));
   DRL_TRY(join_from_side(st, 6));
   g_bwd_launches = n;
   return DRL_OK;

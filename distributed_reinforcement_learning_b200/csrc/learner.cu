@@ -489,6 +489,12 @@ int drl_learner_create(const drl_learner_config* cfg, drl_learner** out) {
     DRL_TRY(dev_alloc(h, &a.logits, M * A));
     DRL_TRY(dev_alloc(h, &a.policy, M * A));
     DRL_TRY(dev_alloc(h, &a.value, M));
+    if (h->mode == 5 && !(getenv("DRL_B200_LSTM_BULK") && atoi(getenv("DRL_B200_LSTM_BULK")) == 0)) {
+      const size_t Mbr = (size_t)h->B * (h->T - 2);
+      DRL_TRY(dev_alloc(h, &a.img_xt, lstm_image_bytes(1, (int)M, (int)Mbr)));
+      DRL_TRY(dev_alloc(h, &h->bwd.img_dzt, lstm_image_bytes(3, (int)M, (int)Mbr)));
+      a.img_rows = (int)M;
+    }
     Bwd& b = h->bwd;
     DRL_TRY(dev_alloc(h, &b.dlogits, Mb * 32));
     DRL_TRY(dev_alloc(h, &b.dv, Mb * 32));
