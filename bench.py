@@ -216,9 +216,10 @@ NCU_TRAFFIC_B32 = {"lstm_fwd": 38.70e6, "lstm_wgrad": 10.25e6, "lstm_dgrad": 37.
 
 
 # the same for the split-16 kernels (math mode 5), from profiles/r02_ncu_umma16_full.md
-NCU_TRAFFIC_B32_M5 = {"conv2_fwd": 32.95e6, "conv3_fwd": 13.47e6, "lstm_fwd": 23.68e6, "lstm_wgrad": 10.24e6,
+# (+ profiles/r02_ncu_conv1_tma.md for the two frame-resident conv1 kernels; lstm_wgrad is the bulk-fed kernel now: not captured)
+NCU_TRAFFIC_B32_M5 = {"conv2_fwd": 32.95e6, "conv3_fwd": 13.47e6, "lstm_fwd": 23.68e6,
                       "lstm_dgrad": 23.78e6, "conv3_wgrad": 19.21e6, "conv3_dgrad": 16.60e6, "conv2_wgrad": 41.74e6,
-                      "conv2_dgrad": 50.96e6}
+                      "conv2_dgrad": 50.96e6, "conv1_fwd": 18.21e6, "conv1_wgrad": 46.13e6}
 
 
 def step_flops(B):
@@ -438,7 +439,8 @@ def run_ours(args):
                 "frac_of_3x16bit_ceiling": ach / (peaks["tf_sus"] / 3.0) if args.math_mode == 5 else None,
                 "traffic": (NCU_TRAFFIC_B32.get(name) if args.math_mode == 2 else
                             NCU_TRAFFIC_B32_M5.get(name) if args.math_mode == 5 else None) if B == 32 else None,
-                "traffic_source": ("profiles/r02_ncu_umma16_full.md" if args.math_mode == 5 else
+                "traffic_source": (("profiles/r02_ncu_conv1_tma.md" if name.startswith("conv1") else
+                                    "profiles/r02_ncu_umma16_full.md") if args.math_mode == 5 else
                                    "profiles/r01_ncu_umma_full.md") + " (ncu --set full, dram read + write per launch)",
                 "peak_source": peaks["src"] + " bf16 sustained",
                 "math_mode": MATH_MODES[args.math_mode] + "; achieved = algorithmic 2MNK flops (counted once, "

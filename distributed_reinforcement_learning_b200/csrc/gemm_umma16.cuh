@@ -593,7 +593,9 @@ template <int BN, class F, class BL>
 inline int launch_retile_b16(cudaStream_t s, const BL& bl, int N, int K, uint8_t* image) {
   const int ntn = cdiv(N, BN), ktiles = cdiv(K, 64);
   const long long units = (long long)ntn * ktiles * BN * 8;
-  DRL_CUDA_CHECK((launch_k(retile_b16_kernel<BN, F, BL>, (unsigned)cdiv64(units, 256), 256, 0, s, bl, N, K, ktiles, ntn, image)));
+  // 128-thread blocks: the images of a step are written beside the persistent conv1 kernel, whose 448 x 128 registers leave
+  // room for 128 threads x 64 registers per SM but not for a 256-thread block (the second image kernel used to wait ~20 us)
+  DRL_CUDA_CHECK((launch_k(retile_b16_kernel<BN, F, BL>, (unsigned)cdiv64(units, 128), 128, 0, s, bl, N, K, ktiles, ntn, image)));
   return DRL_OK;
 }
 

@@ -76,6 +76,8 @@ struct Bwd {             // backward workspace, Mb = B*(T-2) rows
   float* wg_part2;       // split-K partial slabs for the conv1 weight gradient (main stream)
   float* dcol;           // [Mb*81, 512] (conv2) / [Mb*49, 576] (conv3): per-output-pixel tap gradients before col2im
   size_t wg_part_floats;
+  float* emb_scratch = nullptr;   // own scratch of emb_backward (16 * 32 * 256 floats): lets it run on the second side lane
+                                  // beside the conv weight gradients; nullptr: it borrows wg_part on `side`
 };
 
 struct VtraceOut {       // parity taps, batch-major [B, T-2]

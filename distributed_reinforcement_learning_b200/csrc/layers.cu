@@ -105,6 +105,7 @@ int net_forward(const Streams& st, const ParamLayout& pl, const float* P, const 
   // weight images of this step's parameters, all on the side stream: the conv2/conv3 forward ones first (main waits
   // for them behind conv1), the LSTM / dgrad ones behind the embedding table (joined before lstm_fwd)
   const bool m16 = mode == 5;
+  bool c3_event = false;   // conv3's weight image has its own event (math mode 5)
   static const bool heads_tc = !(getenv("DRL_B200_HEADS_TC") && atoi(getenv("DRL_B200_HEADS_TC")) == 0);   // head layers on tcgen05 (0: FFMA)
   // math mode 5: conv1 is the frame-resident TMA kernel (conv1_tma.cuh), which builds its 32 KB weight image itself;
   // DRL_B200_CONV1_GATHER=1 keeps the generic gather-GEMM, DRL_B200_C1_WIMG=1 the pre-tiled image (one more kernel in
@@ -119,8 +120,10 @@ int net_forward(const Streams& st, const ParamLayout& pl, const float* P, const 
       ++n;
     }
     DRL_TRY((launch_retile_b16<64, Fmt16>(s, PlainB{P + pl.conv2_w, 64, 0}, 64, 512, wi.img[1])));
+    if (st.par) DRL_CUDA_CHECK(cudaEventRecord(st.ev[7], side));          // conv2 image (main waits behind conv1)
     DRL_TRY((launch_retile_b16<64, Fmt16>(s, PlainB{P + pl.conv3_w, 64, 0}, 64, 576, wi.img[2])));
-    if (st.par) DRL_CUDA_CHECK(cudaEventRecord(st.ev[7], side));          // conv2 / conv3 images (main waits behind conv1)
+    if (st.par) DRL_CUDA_CHECK(cudaEventRecord(st.ev[4], side));          // conv3 image (main waits behind conv2)
+    c3_event = st.par;
     n += 2;
   } else if (retile && mode >= 2) {
     prof_mark(s, "weight_retile");
@@ -187,6 +190,10 @@ int net_forward(const Streams& st, const ParamLayout& pl, const float* P, const 
     else if (m16 && c2f == 3) GEMM16("conv2_fwd", X64L8x2p4, al, blp, ep, M * 81, 64, 512, 1, 512, 0);
     else if (m16) GEMM16("conv2_fwd", X64L, al, blp, ep, M * 81, 64, 512, 1, 512, 0);
     else GEMM_W("conv2_fwd", CfgBig, U64L, al, bl, blp, ep, M * 81, 64, 512, 1, 512, 0);
+  }
+  if (c3_event) {
+    DRL_CUDA_CHECK(cudaStreamWaitEvent(st.main, st.ev[4], 0));
+    pdl_break(st.main);
   }
   // conv3 -> a3 [M,7,7,64] = flatten HWC [M,3136]   (:8-10)
   if (tma) {
@@ -372,11 +379,25 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, const
     else GEMM_W("lstm_dgrad", CfgMid, U128L, al, bl, blp, ep, Mb, Geo::FLAT + Geo::EMB, Geo::G4, 1, Geo::G4, 0);
   }
   // ---- action embedding + conv3 weight gradient (side) -------------------------------------
+  // the embedding gradient: four small kernels that the hardware schedules late behind the big GEMMs (32 us alone, ~80 us
+  // in the graph).  DRL_B200_EMB_SIDE2=1 moves them to the second lane (own scratch); measured 0.4 % slower than leaving
+  // them in front of conv3_wgrad on `side` (the backward pass is throughput-bound: earlier weight gradients only take SMs
+  // from the main chain), so `side` stays the default.
+  static const bool emb_lane2_on = getenv("DRL_B200_EMB_SIDE2") && atoi(getenv("DRL_B200_EMB_SIDE2")) == 1;
+  const bool emb2 = lane2 && bw.emb_scratch != nullptr && emb_lane2_on;
+  if (emb2) {
+    DRL_TRY(fork_to_side2(st, 3));
+    s = st.side2;
+    KERNEL("emb_bwd",
+           emb_backward(s, bw.du, in.pa, act.e1, act.table, P + pl.emb2_w, bw.dpre2, bw.dpre1, G + pl.emb1_w,
+                        G + pl.emb1_b, G + pl.emb2_w, G + pl.emb2_b, bw.emb_scratch, Mb, B, T, A), 4);
+  }
   DRL_TRY(fork_to_side(st, 4));
   s = side;
-  KERNEL("emb_bwd",
-         emb_backward(s, bw.du, in.pa, act.e1, act.table, P + pl.emb2_w, bw.dpre2, bw.dpre1, G + pl.emb1_w,
-                      G + pl.emb1_b, G + pl.emb2_w, G + pl.emb2_b, bw.wg_part, Mb, B, T, A), 4);
+  if (!emb2)
+    KERNEL("emb_bwd",
+           emb_backward(s, bw.du, in.pa, act.e1, act.table, P + pl.emb2_w, bw.dpre2, bw.dpre1, G + pl.emb1_w,
+                        G + pl.emb1_b, G + pl.emb2_w, G + pl.emb2_b, bw.wg_part, Mb, B, T, A), 4);
   // ---- conv3 -------------------------------------------------------------------------------
   {
     const SplitPlan sp = plan_conv3_wgrad(Mb, mode);
