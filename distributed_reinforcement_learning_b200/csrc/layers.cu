@@ -380,11 +380,13 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, const
   }
   // ---- action embedding + conv3 weight gradient (side) -------------------------------------
   // the embedding gradient: four small kernels that the hardware schedules late behind the big GEMMs (32 us alone, ~80 us
-  // in the graph).  DRL_B200_EMB_SIDE2=1 moves them to the second lane (own scratch); measured 0.4 % slower than leaving
-  // them in front of conv3_wgrad on `side` (the backward pass is throughput-bound: earlier weight gradients only take SMs
-  // from the main chain), so `side` stays the default.
-  static const bool emb_lane2_on = getenv("DRL_B200_EMB_SIDE2") && atoi(getenv("DRL_B200_EMB_SIDE2")) == 1;
-  const bool emb2 = lane2 && bw.emb_scratch != nullptr && emb_lane2_on;
+  // in the graph).  On one GPU they stay in front of conv3_wgrad on `side` (the second lane measured 0.4 % slower: the
+  // backward pass is throughput-bound, earlier weight gradients only take SMs from the main chain).  With the fused peer
+  // exchange the side stream IS the tail of the step (the early exchange part competes with it), and moving them to the
+  // second lane (own scratch) gains 1 % at 2 GPUs.  DRL_B200_EMB_SIDE2=0/1 forces either.
+  static const int emb_lane2_env = getenv("DRL_B200_EMB_SIDE2") ? atoi(getenv("DRL_B200_EMB_SIDE2")) : -1;
+  const bool emb2 = lane2 && bw.emb_scratch != nullptr &&
+                    (emb_lane2_env == 1 || (emb_lane2_env < 0 && st.ev_lstm_grads != nullptr));
   if (emb2) {
     DRL_TRY(fork_to_side2(st, 3));
     s = st.side2;
