@@ -56,7 +56,6 @@ using Fmt16 = umma16::BF16;     // every GEMM whose operands are fp32 activation
 using FmtC1 = umma16::F16;      // conv1: uint8 frames (exact) x weights
 using X32L = Umma16Cfg<32, 4, 2, 4, 1, FmtC1, FmtC1>;        // conv1 fwd: whole K = 256 resident
 using X64L = Umma16Cfg<64, 2, 2, 4, 1, Fmt16, Fmt16>;        // conv2 / conv3 fwd: 48 KB per K = 64 stage, 2 CTAs per SM
-using X64L8 = Umma16Cfg<64, 4, 1, 8, 1, Fmt16, Fmt16>;       // experiment (DRL_B200_C2F=1): one CTA per SM, 8 producer warps, 4 stages
 using X64L8x2 = Umma16Cfg<64, 2, 2, 8, 1, Fmt16, Fmt16>;     // conv2 / conv3 fwd (default): two CTAs per SM x 8 producer warps = twice the loads
                                                              // in flight of X64L (conv2_fwd 41 -> 33 us: the gathers are latency-bound); DRL_B200_C2F=0: X64L
 using X64W8x2 = Umma16Cfg<64, 2, 2, 8, 0, Fmt16, Fmt16>;     // conv2 / conv3 weight gradients (default; 39 -> 33, 30 -> 27 us); DRL_B200_CW8=0: X64W
@@ -66,9 +65,6 @@ using XH = Umma16Cfg<64, 4, 1, 8, 0, Fmt16, Fmt16>;          // head layers (K =
 using BK256 = Bulk16Cfg<256, 2, 8>;    // 96 KB per stage (A 32 KB + B 64 KB), 2 stages
 using X256L = Umma16Cfg<256, 2, 1, 8, 1, Fmt16, Fmt16>;      // lstm fwd: 96 KB per stage
 using X256W = Umma16Cfg<256, 2, 1, 8, 0, Fmt16, Fmt16>;      // lstm weight gradient
-using X256W3 = Umma16Cfg<256, 2, 1, 8, 0, Fmt16, Fmt16, 3>;  // experiment (DRL_B200_LW3=1): two sub-tiles ahead instead of one
-using X64W8x2p3 = Umma16Cfg<64, 2, 2, 8, 0, Fmt16, Fmt16, 3>; // experiment (DRL_B200_CW8=2): deeper prefetch spills at the 96-register cap: slower
-using X64L8x2p4 = Umma16Cfg<64, 2, 2, 8, 1, Fmt16, Fmt16, 4>; // experiment (DRL_B200_C2F=3)
 using X128D = Umma16Cfg<128, 3, 1, 8, 1, Fmt16, Fmt16>;      // lstm data gradient: 64 KB per stage
 using X256D = Umma16Cfg<256, 1, 2, 8, 1, Fmt16, Fmt16>;      // dCol GEMMs (K = 64 = ONE stage of 96 KB): two CTAs per SM, so that
                                                              // the 128 KB epilogue of one overlaps the load + MMAs of the other
@@ -129,9 +125,9 @@ template <> struct PersistOf<U256L> { using type = UmmaPCfg<256, 2, 8>; };
 // DRL_B200_HEADS_KS=1 restores the one-group kernel
 #define GEMM_FFMA_KS(name, SCfg, KS, ...)                      \
   do {                                                       \
-    static const bool one_group = getenv("DRL_B200_HEADS_KS") && atoi(getenv("DRL_B200_HEADS_KS")) == 1; \
+    static const int ks_env = getenv("DRL_B200_HEADS_KS") ? atoi(getenv("DRL_B200_HEADS_KS")) : 0; \
     prof_mark(s, name);                                      \
-    if (one_group) DRL_TRY((launch_gemm_simt<SCfg>(s, __VA_ARGS__)));  \
+    if (ks_env == 1) DRL_TRY((launch_gemm_simt<SCfg>(s, __VA_ARGS__)));  \
     else DRL_TRY((launch_gemm_simt<SCfg, KS>(s, __VA_ARGS__)));        \
     ++n;                                                     \
   } while (0)

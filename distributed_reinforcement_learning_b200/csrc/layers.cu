@@ -185,9 +185,7 @@ int net_forward(const Streams& st, const ParamLayout& pl, const float* P, const 
     PretiledB<PlainB> blp{wi.img[1], m16 ? 512 / 64 : 512 / 32};
     EpBiasAct<true, true> ep{act.a2, 64, 0, P + pl.conv2_b, 0, 1.0f};
     static const int c2f = getenv("DRL_B200_C2F") ? atoi(getenv("DRL_B200_C2F")) : 2;
-    if (m16 && c2f == 1) GEMM16("conv2_fwd", X64L8, al, blp, ep, M * 81, 64, 512, 1, 512, 0);
-    else if (m16 && c2f == 2) GEMM16("conv2_fwd", X64L8x2, al, blp, ep, M * 81, 64, 512, 1, 512, 0);
-    else if (m16 && c2f == 3) GEMM16("conv2_fwd", X64L8x2p4, al, blp, ep, M * 81, 64, 512, 1, 512, 0);
+    if (m16 && c2f == 2) GEMM16("conv2_fwd", X64L8x2, al, blp, ep, M * 81, 64, 512, 1, 512, 0);
     else if (m16) GEMM16("conv2_fwd", X64L, al, blp, ep, M * 81, 64, 512, 1, 512, 0);
     else GEMM_W("conv2_fwd", CfgBig, U64L, al, bl, blp, ep, M * 81, 64, 512, 1, 512, 0);
   }
@@ -206,7 +204,6 @@ int net_forward(const Streams& st, const ParamLayout& pl, const float* P, const 
     EpBiasAct<true, true> ep{act.a3, 64, 0, P + pl.conv3_b, 0, 1.0f};
     static const int c3f = getenv("DRL_B200_C2F") ? atoi(getenv("DRL_B200_C2F")) : 2;
     if (m16 && c3f == 2) GEMM16("conv3_fwd", X64L8x2, al, blp, ep, M * 49, 64, 576, 1, 576, 0);
-    else if (m16 && c3f == 3) GEMM16("conv3_fwd", X64L8x2p4, al, blp, ep, M * 49, 64, 576, 1, 576, 0);
     else if (m16) GEMM16("conv3_fwd", X64L, al, blp, ep, M * 49, 64, 576, 1, 576, 0);
     else GEMM_W("conv3_fwd", CfgBig, U64L, al, bl, blp, ep, M * 49, 64, 576, 1, 576, 0);
   }
@@ -349,7 +346,6 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, const
     LstmAT al{act.a3, act.table, in.pa, in.h0, map};
     PlainB bl{bw.dz, Geo::G4, 0};
     EpRaw<true> ep{G + pl.lstm_w, Geo::G4, 0, 1.0f, Geo::XK, Geo::G4};
-    static const bool lw3 = getenv("DRL_B200_LW3") != nullptr;
     if (lbulk) {
       const int ktm = cdiv(Mb, 64);
       prof_mark(s, "lstm_dzt_image");
@@ -361,8 +357,7 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, const
       DRL_TRY((launch_gemm_bulk16<BK256>(s, ImageOp{act.img_xt, ktm}, ImageOp{bw.img_dzt, ktm}, epw, Geo::XK, Geo::G4, Mb,
                                          1, Mb, 0)));
       n += 3;
-    } else if (m16 && lw3) GEMM16("lstm_wgrad", X256W3, al, bl, ep, Geo::XK, Geo::G4, Mb, 1, Mb, 0);
-    else if (m16) GEMM16("lstm_wgrad", X256W, al, bl, ep, Geo::XK, Geo::G4, Mb, 1, Mb, 0);
+    } else if (m16) GEMM16("lstm_wgrad", X256W, al, bl, ep, Geo::XK, Geo::G4, Mb, 1, Mb, 0);
     else GEMM("lstm_wgrad", CfgBig, U256, al, bl, ep, Geo::XK, Geo::G4, Mb, 1, Mb, 0);   // 29 x 4 = 116 CTAs: one wave
     // the head gradients (earlier on this stream, or on the second lane: joined here) and the LSTM gradient are now
     // in the bucket: [lstm_w .. end)
@@ -408,8 +403,7 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, const
     PlainB bl{bw.da3, 64, 0};
     EpRaw<true> ep{bw.wg_part, 64, slab, 1.0f, 576, 64};
     static const int cw8 = getenv("DRL_B200_CW8") ? atoi(getenv("DRL_B200_CW8")) : 1;
-    if (m16 && cw8 == 2) GEMM16("conv3_wgrad", X64W8x2p3, al, bl, ep, 576, 64, Mb * 49, sp.splits, sp.kchunk, sp.kchunk);
-    else if (m16 && cw8) GEMM16("conv3_wgrad", X64W8x2, al, bl, ep, 576, 64, Mb * 49, sp.splits, sp.kchunk, sp.kchunk);
+    if (m16 && cw8) GEMM16("conv3_wgrad", X64W8x2, al, bl, ep, 576, 64, Mb * 49, sp.splits, sp.kchunk, sp.kchunk);
     else if (m16) GEMM16("conv3_wgrad", X64W, al, bl, ep, 576, 64, Mb * 49, sp.splits, sp.kchunk, sp.kchunk);
     else GEMM("conv3_wgrad", CfgBig, U64, al, bl, ep, 576, 64, Mb * 49, sp.splits, sp.kchunk, sp.kchunk);
     KERNEL("conv3_wgrad_reduce", splitk_reduce(s, bw.wg_part, slab, sp.splits, G + pl.conv3_w, slab), 1);
@@ -454,8 +448,7 @@ int net_backward(const Streams& st, const ParamLayout& pl, const float* P, const
     PlainB bl{bw.da2, 64, 0};
     EpRaw<true> ep{bw.wg_part, 64, slab, 1.0f, 512, 64};
     static const int cw8 = getenv("DRL_B200_CW8") ? atoi(getenv("DRL_B200_CW8")) : 1;
-    if (m16 && cw8 == 2) GEMM16("conv2_wgrad", X64W8x2p3, al, bl, ep, 512, 64, Mb * 81, sp.splits, sp.kchunk, sp.kchunk);
-    else if (m16 && cw8) GEMM16("conv2_wgrad", X64W8x2, al, bl, ep, 512, 64, Mb * 81, sp.splits, sp.kchunk, sp.kchunk);
+    if (m16 && cw8) GEMM16("conv2_wgrad", X64W8x2, al, bl, ep, 512, 64, Mb * 81, sp.splits, sp.kchunk, sp.kchunk);
     else if (m16) GEMM16("conv2_wgrad", X64W, al, bl, ep, 512, 64, Mb * 81, sp.splits, sp.kchunk, sp.kchunk);
     else GEMM("conv2_wgrad", CfgBig, U64, al, bl, ep, 512, 64, Mb * 81, sp.splits, sp.kchunk, sp.kchunk);
     KERNEL("conv2_wgrad_reduce", splitk_reduce(s, bw.wg_part, slab, sp.splits, G + pl.conv2_w, slab), 1);
