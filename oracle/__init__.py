@@ -19,7 +19,7 @@ in this image (no wheel for CPython 3.12, no network), and it ships no tests, go
 reference's OWN FILES are nevertheless executed here: ``oracle/tf1_shim/tensorflow`` implements the slice of the TF1
 API those files touch as a deferred graph over torch-CPU, ``oracle/ref_exec.py`` imports the unmodified
 ``agent/impala.py``, ``optimizer/vtrace.py``, ``model/impala_actor_critic.py``, ``distributed_queue/buffer_queue.py``
-(and the Ape-X / R2D2 files) from the checkout, and ``tests/test_oracle_refexec.py`` asserts that every restatement in
+(and the Ape-X / R2D2 / A3C files) from the checkout, and ``tests/test_oracle_refexec.py`` asserts that every restatement in
 this package equals the executed reference (V-trace taps, losses, all gradients, optimizer steps with slots, variable
 names / sharing, parameter_sync, queue order) to ~1e-12 in float64.  ``tests/golden/*.npz`` are written from those
 executed-reference runs (``tests/golden/make_golden.py``).  What remains restated rather than executed is TF's own op

@@ -1,6 +1,7 @@
-"""PyTorch-CPU restatement of the reference A3C learner step -- TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED for this
-family (outside SURVEY.md section 8: the executed-reference pin of ``oracle/ref_exec.py`` covers IMPALA, Ape-X and R2D2; TensorFlow
-1.14 is not installable, the reference ships no tests); float64 = truth, float32 = CPU baseline.
+"""PyTorch-CPU restatement of the reference A3C learner step -- TEST INFRASTRUCTURE ONLY.  PINNED:
+``tests/test_oracle_refexec.py`` executes the unmodified ``agent/a3c.py`` / ``model/actor_critic.py`` / ``optimizer/a2c.py`` over
+``oracle/tf1_shim`` and this restatement equals it (policy, values, the three losses, all 22 gradients to ~1e-12, three Adam steps;
+TensorFlow 1.14 itself is not installable here -- see ``oracle/__init__.py``); float64 = truth, float32 = CPU baseline.
 
 Follows:
   model/actor_critic.py:3-39   attention_CNN / action_embedding / fully_connected / network -> ``network``

@@ -262,3 +262,68 @@ class ReferenceR2D2(_TwoScopeAgent):
     def fetch(self, batch_args, names):
         a = self.agent
         return dict(zip(names, self.sess.run([getattr(a, n) for n in names], feed_dict=self.feed(*batch_args))))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# A3C learner through the reference's own Agent (agent/a3c.py:9-103): one scope <model_name>/a3c, variables shared by
+# network(s, a_prev) and network(s', a) (model/actor_critic.py:41-56)
+# ----------------------------------------------------------------------------------------------------------------
+A3C_VAR_ORDER = (("conv2d", "conv1"), ("conv2d_1", "conv2"), ("conv2d_2", "conv3"), ("dense", "emb1"),
+                 ("dense_1", "emb2"), ("dense_2", "actor1"), ("dense_3", "actor2"), ("dense_4", "actor3"),
+                 ("dense_5", "critic1"), ("dense_6", "critic2"), ("dense_7", "critic3"))
+
+
+class ReferenceA3C:
+    def __init__(self, params, float_dtype=None, **cfg):
+        import torch
+        from oracle import a3c_torch as a3
+        self.ref = load(("agent.a3c", "model.actor_critic", "optimizer.a2c", "utils"),
+                        float_dtype=float_dtype or torch.float64)
+        tf = self.ref.tf
+        c = dict(a3.DEFAULT_CFG)
+        c.update(cfg)
+        self.cfg = c
+        self.agent = self.ref["agent.a3c"].Agent(
+            input_shape=list(c["input_shape"]), num_action=c["num_action"], discount_factor=c["discount_factor"],
+            start_learning_rate=c["start_learning_rate"], end_learning_rate=c["end_learning_rate"],
+            learning_frame=c["learning_frame"], baseline_loss_coef=c["baseline_loss_coef"],
+            entropy_coef=c["entropy_coef"], gradient_clip_norm=c["gradient_clip_norm"],
+            reward_clipping=c["reward_clipping"], model_name="learner", learner_name="learner")
+        self.sess = tf.Session()
+        self.agent.set_session(self.sess)
+        self.var, expect = {}, []
+        for tf_name, our in A3C_VAR_ORDER:
+            for kind, suffix in (("kernel", ".w"), ("bias", ".b")):
+                full = "learner/a3c/%s/%s" % (tf_name, kind)
+                expect.append(full)
+                self.var[our + suffix] = tf.get_default_graph().var_by_name[full]
+        names = [v.op_name for v in tf.trainable_variables()]
+        assert names == expect, "variable creation order differs from the oracle's parameter order: %r" % (names,)
+        for n, v in params.items():
+            assert tuple(self.var[n]._shape) == tuple(v.shape), (n, self.var[n]._shape, tuple(v.shape))
+            self.var[n].set(v.detach().to(torch.float32).numpy())
+
+    def feed(self, state, next_state, previous_action, action, reward, done):
+        """feed_dict of Agent.train (agent/a3c.py:86-101): next_previous_action = action."""
+        import numpy as np
+        a = self.agent
+        return {a.s_ph: np.stack(state) / 255, a.ns_ph: np.stack(next_state) / 255, a.pa_ph: previous_action,
+                a.npa_ph: action, a.a_ph: action, a.r_ph: reward, a.d_ph: done}
+
+    def fetch(self, batch_args, names):
+        a = self.agent
+        return dict(zip(names, self.sess.run([getattr(a, n) for n in names], feed_dict=self.feed(*batch_args))))
+
+    def gradients(self, batch_args):
+        tf = self.ref.tf
+        if not hasattr(self, "_grad_nodes"):
+            self._grad_nodes = tf.gradients(self.agent.total_loss, [self.var[n] for n in self.var])
+        return dict(zip(self.var, self.sess.run(self._grad_nodes, feed_dict=self.feed(*batch_args))))
+
+    def params(self):
+        return {n: v.numpy() for n, v in self.var.items()}
+
+    def adam_slots(self):
+        opt = self.agent.optimizer
+        return ({n: opt.get_slot(v, "m").numpy() for n, v in self.var.items()},
+                {n: opt.get_slot(v, "v").numpy() for n, v in self.var.items()})

@@ -397,3 +397,37 @@ def test_reference_sumtree_and_memory_executed_equal_restatement_and_native():
         assert rmem.tree.total() == omem.tree.total()
         if nmem is not None:
             assert nmem.tree.total() == rmem.tree.total()
+
+
+# ---- agent/a3c.py + model/actor_critic.py + optimizer/a2c.py (the fourth learner family) ---------------------------
+@pytest.mark.parametrize("clipping", ["abs_one", "soft_asymmetric"])
+def test_a3c_executed_reference_equals_restatement(clipping):
+    from oracle import a3c_torch as a3
+    A = 5
+    b = a3.make_transitions(4, A=A, seed=97)
+    b["reward"] = (b["reward"] * 3).astype(np.float32)            # both branches of either clipping
+    p = a3.init_params(0, torch.float32, num_action=A)
+    R = ref_exec.ReferenceA3C(p, num_action=A, reward_clipping=clipping)
+    L = a3.Learner(p, torch.float64, num_action=A, reward_clipping=clipping)
+    args = [b[k] for k in a3.TRAIN_FIELDS]
+    out = L.losses(*args)
+    f = R.fetch(args, ["policy", "value", "next_value", "pi_loss", "baseline_loss", "entropy", "total_loss"])
+    for k in ("policy", "value", "next_value"):
+        assert _rel(out[k].detach().numpy(), f[k]) < 1e-12, k
+    for k in ("pi_loss", "baseline_loss", "entropy", "total_loss"):
+        assert float(out[k].detach()) == pytest.approx(float(f[k]), rel=1e-12), k
+    rg = R.gradients(args)
+    names = list(L.params)
+    g = torch.autograd.grad(out["total_loss"], [L.params[n] for n in names], allow_unused=True)
+    assert len(rg) == 22
+    for n, gi in zip(names, g):
+        assert _rel(gi.numpy(), rg[n]) < 1e-11, n
+    # three Agent.train calls: poly-decay lr, clip_by_global_norm 40, Adam with float32 beta powers
+    for _ in range(3):
+        r1, r2 = R.agent.train(*args), L.train(*args)
+        for x, y in zip(r1, r2):
+            assert float(x) == pytest.approx(float(y), rel=1e-6, abs=1e-12)
+    for n, v in R.params().items():
+        assert _rel(v, L.params[n].detach().numpy()) < 1e-6, n
+    m, v = R.adam_slots()
+    assert max(_rel(m[n], L.m[n].numpy()) for n in m) < 1e-5 and max(_rel(v[n], L.v[n].numpy()) for n in v) < 1e-5
