@@ -1,7 +1,6 @@
 """Generates the committed golden vectors of the IMPALA learner step, of optimizer/vtrace.py and of the Ape-X / R2D2
 steps by EXECUTING THE UNMODIFIED REFERENCE FILES (``/root/reference/agent/impala.py`` etc.) over the TF 1.14 API
-stand-in ``oracle/tf1_shim`` in float64 (``oracle/ref_exec.py``); the A3C vectors (out of scope) still come from its
-float64 restatement.
+stand-in ``oracle/tf1_shim`` in float64 (``oracle/ref_exec.py``), the A3C family included.
 
     python tests/golden/make_golden.py [impala] [vtrace] [apex] [r2d2] [a3c]     # default: all; writes tests/golden/*.npz
 
@@ -128,14 +127,23 @@ def r2d2_case(path, B=2, S=6, bi=2, seed=2468):
 
 
 def a3c_case(path, B=3, A=4, seed=97531):
+    """agent/a3c.py:85-103 ``Agent.train`` executed once (inputs regenerated from make_transitions(B, A, seed), parameters
+    from init_params(0)); taps and gradients fetched from the agent's own graph."""
     from oracle import a3c_torch as at
+    from oracle import ref_exec
     b = at.make_transitions(B, A=A, seed=seed)
-    L = at.Learner(dtype=torch.float64, num_action=A)
-    (pi, bl, en, lr), out, g, gn = L.train(*[b[k] for k in at.TRAIN_FIELDS], return_all=True)
-    rec = dict(B=B, A=A, seed=seed, pi_loss=pi, baseline_loss=bl, entropy=en, learning_rate=lr, grad_norm=gn,
-               source="oracle/a3c_torch.py (float64 restatement; A3C is out of scope, not executed from the reference)")
-    for k in ("policy", "value", "next_value", "advantage"):
-        rec[k] = out[k].detach().numpy()
+    p = at.init_params(0, torch.float32, num_action=A)
+    R = ref_exec.ReferenceA3C(p, num_action=A)
+    args = [b[k] for k in at.TRAIN_FIELDS]
+    f = R.fetch(args, ["policy", "value", "next_value", "clipped_r_ph", "discounts"])
+    g = R.gradients(args)
+    gn = float(np.sqrt(sum(np.sum(np.asarray(v, np.float64) ** 2) for v in g.values())))
+    pi, bl, en, lr = R.agent.train(*args)
+    rec = dict(B=B, A=A, seed=seed, pi_loss=float(pi), baseline_loss=float(bl), entropy=float(en), learning_rate=float(lr),
+               grad_norm=gn, source=SOURCE)
+    for k in ("policy", "value", "next_value"):
+        rec[k] = np.asarray(f[k])
+    rec["advantage"] = np.asarray(f["clipped_r_ph"]) + np.asarray(f["discounts"]) * rec["next_value"] - rec["value"]
     _pack_grads(rec, g)
     np.savez_compressed(path, **rec)
     return rec
