@@ -243,7 +243,7 @@ def usable_cores():
     return max(1, n)
 
 
-def cpu_reference(steps, warmup, B=B_PER_GPU, global_batch=None):
+def cpu_reference(steps, warmup, B=B_PER_GPU, global_batch=None, budget_s=10.0):
     import torch
     from oracle import impala_torch as it
     from oracle import synthetic
@@ -255,10 +255,13 @@ def cpu_reference(steps, warmup, B=B_PER_GPU, global_batch=None):
     for _ in range(warmup):
         Lr.train(*args)
     ts = []
-    for _ in range(steps):
+    # steps = None: a time-bounded sample (the cpu_baseline leg of the default run): at least 3 steps, then as many as
+    # fit into ~10 s of CPU work (task section 4: "about 10-30 s of CPU work"), at most 64
+    while (len(ts) < steps) if steps is not None else (len(ts) < 3 or (sum(ts) < budget_s and len(ts) < 64)):
         t0 = time.perf_counter()
         Lr.train(*args)
         ts.append(time.perf_counter() - t0)
+    steps = len(ts)
     sec = float(np.sum(ts)) / max(len(ts), 1)
     return dict(value=B * T / sec, unit="frames/s", cores=cores, kind="port", ms_per_step=sec * 1e3,
                 sample="%d timed steps (+%d warm-up) of the float32 torch-CPU restatement of the reference graph "
@@ -459,7 +462,7 @@ def run_ours(args):
         except Exception as ex:      # pragma: no cover
             line_extra["roofline_vtrace_b32"] = {"error": str(ex)}
         if args.cpu_baseline and world == 1:      # rank 0 at N=1 only
-            line_extra["cpu_baseline"] = cpu_reference(3, 1, min(B, 32), B)
+            line_extra["cpu_baseline"] = cpu_reference(None, 1, min(B, 32), B)
     if world > 1:
         dist.barrier()           # peers' buffers stay mapped until everybody is done
     eng.close()
