@@ -64,8 +64,10 @@ typedef struct drl_learner_config {
   int32_t device;             /* CUDA device ordinal                                            */
   int32_t num_slots;          /* device staging slots for stream-overlapped H2D (>=1, default 2) */
   int32_t use_cuda_graph;     /* 1: capture forward+backward(+apply) into CUDA graphs           */
-  int32_t math_mode;          /* 0 = default (2); 1 = FP32 FFMA; 2 = tcgen05 3xTF32; 3 = same, persistent kernels;
-                                 4 = as 2 with TMA-fed conv2/conv3 forward (experimental) */
+  int32_t math_mode;          /* 0 = default (5); 1 = FP32 FFMA; 2 = tcgen05 3xTF32; 3 = same, persistent kernels;
+                                 4 = as 2 with TMA-fed conv2/conv3 forward (experimental); 5 = tcgen05 kind::f16 on
+                                 bf16 hi/lo split operands (three products, fp32-grade) + TMA-fed conv1 kernels +
+                                 bulk-fed LSTM weight gradient */
 } drl_learner_config;
 
 /* Results of one step: the 4 floats Agent.train returns (agent/impala.py:144-148) + grad norm. */
